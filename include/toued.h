@@ -1,0 +1,60 @@
+/* toued.h — C ABI of the B200-native TO-UED / GROOVE meta-training hot path.
+ *
+ * The reference (nmonette/TO-UED) is a pure-JAX program with no plugin / operator / FFI layer
+ * (SURVEY.md §8b); the de-facto boundary is its Python call signatures.  Each entry point below is
+ * the device-side operation one of those Python functions performs; the Python mirror in
+ * to_ued_b200/ keeps the reference names and argument meaning and binds these with ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; plain C types only;
+ *   - `stream` is the caller's cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - no entry point allocates device memory or synchronises; all work is enqueued on `stream`;
+ *   - return 0 on success, non-zero on error; toued_last_error() gives the message (thread-local);
+ *   - layouts: "agent" axis N, "worker" axis W, time axis L.  Trajectories are [N][L][W]
+ *     (obs: [N][L+1][W]); tables are [N][D][8] floats (actor rows padded 5 -> 8, critic rows = 8).
+ */
+#ifndef TOUED_H
+#define TOUED_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOUED_LEVEL_BYTES 192   /* sizeof(LevelRec), see to_ued_b200/csrc/common.cuh */
+
+const char* toued_last_error(void);
+int toued_version(void);
+
+/* environments/rollout.py:45-102 RolloutWrapper.batch_rollout (+ :38-42 batch_reset when
+ * reset_first != 0) fused with environments/gridworld/gridworld.py:72-211 and the tabular Actor
+ * of models/agent.py:7-17.
+ *   levels          LevelRec[N]           packed EnvParams (+ lifetime, buffer_id)
+ *   keys            u32[N][2]             the per-agent key passed to batch_rollout
+ *   actor           f32[N][D][8]          actor tables
+ *   forced_actions  u8[N][L][W] or NULL   replay a given action stream instead of sampling
+ *   state           i32[N][W] in/out      packed EnvState (pos | exists<<8 | time<<16); may be NULL
+ *                                         when reset_first != 0 and the end state is not wanted
+ *   obs             i32[N][L+1][W] out    packed observations (row | time<<16); NULL = no trajectory
+ *   action,done     u8[N][L][W] out ; reward f32[N][L][W] out
+ *   ep_return       f32[N][W] out or NULL first-episode return (rollout.py:68-69)               */
+int toued_rollout(const void* levels, const uint32_t* keys, const float* actor,
+                  const uint8_t* forced_actions, int32_t* state, int32_t* obs, uint8_t* action,
+                  float* reward, uint8_t* done, float* ep_return, int n_agents, int n_workers,
+                  int rollout_len, int obs_dim, int max_grid_size, int max_n_objs, int reset_first,
+                  void* stream);
+
+/* gymnax-style single transitions: environments/gridworld/gridworld.py:72-182 behind
+ * gymnax==0.0.6 Environment.step (key split + auto-reset) / Environment.reset.
+ *   keys u32[N][W][2] per-env step keys ; actions i32[N][W] ; state i32[N][W] in/out ;
+ *   obs i32[N][W] out ; reward f32[N][W] out ; done u8[N][W] out                                */
+int toued_env_step(const void* levels, const uint32_t* keys, const int32_t* actions, int32_t* state,
+                   int32_t* obs, float* reward, uint8_t* done, int n_agents, int n_workers,
+                   int max_grid_size, int max_n_objs, void* stream);
+int toued_env_reset(const void* levels, int32_t* state, int32_t* obs, int n_agents, int n_workers,
+                    int max_grid_size, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,73 @@
+"""ctypes binding of libtoued.so (the C ABI in include/toued.h).
+
+There is no CPU fallback: importing this module without the built library, or calling an op
+without a CUDA device, raises.  Build with ``python -m to_ued_b200.csrc.build`` (or
+``__graft_entry__.build()``)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtoued.so")
+
+_lib = None
+
+
+class TouedError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TouedError(
+                f"{LIB_PATH} is missing: the CUDA extension is not built. "
+                "Run `python -m to_ued_b200.csrc.build` (there is no CPU fallback).")
+        _lib = C.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+_P, _I = C.c_void_p, C.c_int
+
+# name -> argtypes; every function returns int except the two below
+SIGNATURES = {
+    "toued_rollout": [_P] * 10 + [_I] * 7 + [_P],
+    "toued_env_step": [_P] * 7 + [_I] * 4 + [_P],
+    "toued_env_reset": [_P] * 3 + [_I] * 3 + [_P],
+}
+
+
+def _declare(l):
+    l.toued_last_error.restype = C.c_char_p
+    l.toued_last_error.argtypes = []
+    l.toued_version.restype = _I
+    l.toued_version.argtypes = []
+    for name, args in SIGNATURES.items():
+        fn = getattr(l, name)
+        fn.restype = _I
+        fn.argtypes = args
+
+
+def ptr(t):
+    """device pointer of a torch tensor (None -> NULL).  Refuses CPU tensors: no fallback."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise TouedError("to_ued_b200 ops need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise TouedError("to_ued_b200 ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise TouedError(f"{name} failed ({rc}): {lib().toued_last_error().decode()}")

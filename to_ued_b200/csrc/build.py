@@ -1,0 +1,51 @@
+"""Build libtoued.so (sm_100a) in-tree with nvcc.  Used by __graft_entry__.build() and importable
+as ``python -m to_ued_b200.csrc.build``.  One object per .cu so only changed files recompile."""
+import os, subprocess, sys, hashlib, shutil
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "..", "libtoued.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--use_fast_math"]
+# per-file overrides: the sampling path must round exactly like the oracle (no FMA contraction,
+# IEEE division), so rollout.cu drops --use_fast_math and adds -fmad=false.
+FLAGS = {
+    "rollout.cu": ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-fmad=false"],
+}
+
+
+def _nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def build(verbose=False, force=False):
+    srcs = sorted(f for f in os.listdir(HERE) if f.endswith(".cu"))
+    hdrs = sorted(f for f in os.listdir(HERE) if f.endswith(".cuh")) + ["../../include/toued.h"]
+    hsig = hashlib.sha1(b"".join(open(os.path.join(HERE, h), "rb").read() for h in hdrs)).hexdigest()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs, rebuilt = [], False
+    for s in srcs:
+        src = os.path.join(HERE, s)
+        obj = os.path.join(objdir, s[:-3] + ".o")
+        flags = FLAGS.get(s, COMMON)
+        sig = hashlib.sha1(open(src, "rb").read() + hsig.encode() + " ".join(flags).encode()).hexdigest()
+        sigf = obj + ".sig"
+        if force or not os.path.exists(obj) or not os.path.exists(sigf) or open(sigf).read() != sig:
+            cmd = [_nvcc(), *ARCH, *flags, "-c", src, "-o", obj]
+            if verbose:
+                cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+            open(sigf, "w").write(sig)
+            rebuilt = True
+        objs.append(obj)
+    if rebuilt or not os.path.exists(OUT):
+        cmd = [_nvcc(), *ARCH, "-shared", "-o", OUT, *objs, "-lcudart"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return os.path.abspath(OUT)
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
