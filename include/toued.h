@@ -54,6 +54,41 @@ int toued_env_step(const void* levels, const uint32_t* keys, const int32_t* acti
 int toued_env_reset(const void* levels, int32_t* state, int32_t* obs, int n_agents, int n_workers,
                     int max_grid_size, void* stream);
 
+/* ---- LPG-driven agent update (agents/lpg_agent.py:31-140, models/lpg.py:11-85) ----------------
+ * LPG tensors are time-major [L][R] with R = N*W, row = n*W + w.
+ * lpg_params: the flat parameter vector, layout in to_ued_b200/csrc/lpg_common.cuh.              */
+
+/* Stable per-agent sort of the W*L tokens by observation row; sorted_tok u16[N][W*L] holds token
+ * ids t*W+w.  Makes every later row scatter a deterministic segmented sum.                      */
+int toued_sort_tokens(const int32_t* obs, uint16_t* sorted_tok, int n_agents, int n_workers,
+                      int rollout_len, void* stream);
+
+/* lpg_agent.py:46-58 + lpg.py:64-76: actor/critic forward on obs & next_obs, embedding MLP, LPG
+ * input rows x f32[L][R][8] = [r, d, pi+1e-8, pyt, pyt1*(1-d), step|0, lifetime|0, 1].            */
+int toued_lpg_prepare(const int32_t* obs, const uint8_t* action, const float* reward,
+                      const uint8_t* done, const float* actor, const float* critic,
+                      const float* lpg_params, const int32_t* step, const void* levels, float* x,
+                      int n_agents, int n_workers, int rollout_len, int obs_dim,
+                      int lifetime_conditioning, void* stream);
+
+/* lpg.py:11-30,77-84: reverse GRU with done-reset, relu, heads.  Exact-fp32 SIMT path.
+ *   h_out f32[L][R][256]; gates f32[4][L][R][256] (r, z, n, Whn h + bhn) or NULL;
+ *   pi_hat f32[L][R]; y_hat f32[L][R][8]                                                          */
+int toued_gru_forward(const float* x, const uint8_t* done, const float* lpg_params, float* h_out,
+                      float* gates, float* pi_hat, float* y_hat, int n_agents, int n_workers,
+                      int rollout_len, int lifetime_conditioning, void* stream);
+
+/* lpg_agent.py:60-85,119-120 + optim.py:6-11: closed-form actor/critic gradients, clip-by-global-
+ * norm SGD, lifetime mask, step += keep, entropies of the updated nets.
+ *   scalars f32[N][8] = {|g_actor|, |g_critic|, keep, critic_loss, pi_l2, y_l2, policy_entropy,
+ *                        critic_entropy}                                                          */
+int toued_agent_update(const int32_t* obs, const uint8_t* action, const uint16_t* sorted_tok,
+                       const float* pi_hat, const float* y_hat, const float* actor_in,
+                       const float* critic_in, float* actor_out, float* critic_out,
+                       const void* levels, int32_t* step, float* scalars, int n_agents,
+                       int n_workers, int rollout_len, int obs_dim, float lr_actor, float lr_critic,
+                       float max_grad_norm, float agent_target_coeff, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

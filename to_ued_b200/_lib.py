@@ -30,13 +30,17 @@ def lib() -> C.CDLL:
     return _lib
 
 
-_P, _I = C.c_void_p, C.c_int
+_P, _I, _F = C.c_void_p, C.c_int, C.c_float
 
 # name -> argtypes; every function returns int except the two below
 SIGNATURES = {
     "toued_rollout": [_P] * 10 + [_I] * 7 + [_P],
     "toued_env_step": [_P] * 7 + [_I] * 4 + [_P],
     "toued_env_reset": [_P] * 3 + [_I] * 3 + [_P],
+    "toued_sort_tokens": [_P] * 2 + [_I] * 3 + [_P],
+    "toued_lpg_prepare": [_P] * 10 + [_I] * 5 + [_P],
+    "toued_gru_forward": [_P] * 7 + [_I] * 4 + [_P],
+    "toued_agent_update": [_P] * 12 + [_I] * 4 + [_F] * 4 + [_P],
 }
 
 

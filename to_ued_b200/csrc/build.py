@@ -5,9 +5,9 @@ import os, subprocess, sys, hashlib, shutil
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "..", "libtoued.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--use_fast_math"]
-# per-file overrides: the sampling path must round exactly like the oracle (no FMA contraction,
-# IEEE division), so rollout.cu drops --use_fast_math and adds -fmad=false.
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+# per-file overrides: the sampling path must round exactly like the oracle (no FMA contraction),
+# so rollout.cu adds -fmad=false.
 FLAGS = {
     "rollout.cu": ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-fmad=false"],
 }
