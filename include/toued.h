@@ -89,6 +89,58 @@ int toued_agent_update(const int32_t* obs, const uint8_t* action, const uint16_t
                        int n_workers, int rollout_len, int obs_dim, float lr_actor, float lr_critic,
                        float max_grad_norm, float agent_target_coeff, void* stream);
 
+/* ---- meta-gradient (meta/train.py:14-130): what the reference gets from jax.grad ---------------- */
+
+/* meta/train.py:60-100 on the eval rollout: GAE with the (frozen, Q2) value critic, advantage
+ * normalisation, LPG loss (outer_product_quirk != 0 reproduces Q16), and the adjoint of theta_K.
+ *   value_table f32[N][D][value_stride] (column 0 used) ; lam, mu f32[N][D][8] out (mu zeroed)
+ *   scalars f32[N][2] = {lpg_loss, value_loss} ; grad_scale = 1 / (global number of agents)        */
+int toued_meta_loss(const int32_t* obs, const uint8_t* action, const float* reward,
+                    const uint8_t* done, const uint16_t* sorted_tok, const float* value_table,
+                    const float* actor, float* lam, float* mu, float* scalars, int n_agents,
+                    int n_workers, int rollout_len, int obs_dim, int value_stride, float gamma,
+                    float gae_lambda, float grad_scale, int outer_product_quirk, void* stream);
+
+/* Adjoint of agent update k (lpg_agent.py:60-82 under jax.grad): entropy regularisers at the updated
+ * tables, Hessian-vector products through grad/clip/SGD/lifetime-mask, cotangents of pi_hat, y_hat.
+ * The four regulariser coefficients are passed already divided by K (mean over the K updates).
+ *   update_scalars: the f32[N][8] written by toued_agent_update for this k ; lam, mu in/out        */
+int toued_agent_backward(const int32_t* obs, const uint8_t* action, const uint16_t* sorted_tok,
+                         const float* pi_hat, const float* y_hat, const float* actor_k,
+                         const float* critic_k, const float* actor_k1, const float* critic_k1,
+                         const float* update_scalars, float* lam, float* mu, float* d_pi_hat,
+                         float* d_y_hat, int n_agents, int n_workers, int rollout_len, int obs_dim,
+                         float lr_actor, float lr_critic, float max_grad_norm,
+                         float agent_target_coeff, float policy_entropy_coeff,
+                         float target_entropy_coeff, float policy_l2_coeff, float target_l2_coeff,
+                         float grad_scale, void* stream);
+
+/* whT f32[768][256] = transpose of the recurrent matrix Wh (once per meta-step).                 */
+int toued_transpose_wh(const float* lpg_params, float* whT, void* stream);
+
+/* BPTT through heads + reverse GRU (models/lpg.py:11-30,77-84).  gates f32[4][L][R][256] is
+ * overwritten in place with (dar, daz, dan, dhn); dl f32[L][R][8] (head logit cotangents) and
+ * dx f32[L][R][2] (d pyt, d pyt1) are outputs.                                                    */
+int toued_gru_backward(const uint8_t* done, const float* lpg_params, const float* whT,
+                       const float* h, float* gates, const float* y_hat, const float* d_pi_hat,
+                       const float* d_y_hat, float* dl, float* dx, int n_agents, int n_workers,
+                       int rollout_len, int lifetime_conditioning, void* stream);
+
+/* Parameter gradients of one update as deterministic token-split partial sums in `workspace`
+ * (toued_lpg_wgrad_workspace_floats() floats); accumulate != 0 adds to the partials of earlier
+ * updates.  toued_reduce_partials then writes the flat gradient f32[P].                            */
+int toued_lpg_wgrad_workspace_floats(void);
+int toued_lpg_wgrad(const int32_t* obs, const uint8_t* done, const float* critic,
+                    const float* lpg_params, const float* x, const float* h, const float* dgates,
+                    const float* d_pi_hat, const float* dl, const float* dx, float* workspace,
+                    int n_agents, int n_workers, int rollout_len, int obs_dim,
+                    int lifetime_conditioning, int accumulate, void* stream);
+int toued_reduce_partials(const float* workspace, float* grad, int lifetime_conditioning, void* stream);
+
+/* models/optim.py:12-17: optax.scale_by_adam -> scale(lr) -> scale(-1); count is 1-based.          */
+int toued_adam(float* params, const float* grad, float* mu, float* nu, int n, int count, float lr,
+               float b1, float b2, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

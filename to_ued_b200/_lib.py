@@ -41,6 +41,14 @@ SIGNATURES = {
     "toued_lpg_prepare": [_P] * 10 + [_I] * 5 + [_P],
     "toued_gru_forward": [_P] * 7 + [_I] * 4 + [_P],
     "toued_agent_update": [_P] * 12 + [_I] * 4 + [_F] * 4 + [_P],
+    "toued_meta_loss": [_P] * 10 + [_I] * 5 + [_F] * 3 + [_I, _P],
+    "toued_agent_backward": [_P] * 14 + [_I] * 4 + [_F] * 9 + [_P],
+    "toued_transpose_wh": [_P] * 3,
+    "toued_gru_backward": [_P] * 10 + [_I] * 4 + [_P],
+    "toued_lpg_wgrad_workspace_floats": [],
+    "toued_lpg_wgrad": [_P] * 11 + [_I] * 6 + [_P],
+    "toued_reduce_partials": [_P, _P, _I, _P],
+    "toued_adam": [_P] * 4 + [_I, _I] + [_F] * 4 + [_P],
 }
 
 

@@ -1,0 +1,217 @@
+"""LPG meta-optimisation steps (reference meta/train.py:14-227) on the B200 kernels.
+
+``lpg_meta_grad_train_step`` keeps the reference's keyword signature.  Where the reference takes
+``jax.grad`` of the unrolled inner loop, this runs the hand-written reverse pass:
+
+    forward  (per update k)  rollout -> sort tokens -> LPG inputs -> GRU + heads -> agent update
+    eval rollout with theta_K -> meta loss (GAE with the frozen value critic, Q2; LPG loss, Q16) -> lam_K
+    backward (k = K-1 .. 0)  agent adjoint (HVPs through clip/SGD/mask) -> d pi_hat, d y_hat
+                             -> GRU BPTT -> token-split weight-gradient partials
+    reduce partials -> (all-reduce over ranks) -> Adam
+
+Agents are the data-parallel axis: with torch.distributed initialised, every rank holds
+``num_agents / world_size`` agents and the flat LPG gradient plus the metric sums are all-reduced
+(one NCCL call each); ``num_mini_batches`` (a memory device in the reference, util/jax.py:25-41)
+splits the local agents into sequential chunks whose partial sums accumulate, giving identical
+results."""
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..util import prng
+from ..util.data import AgentState, LpgHyperparams
+from ..agents.lpg_agent import Tape, train_lpg_agent
+from ..agents.agents import eval_agent
+from ..environments.gridworld.gridworld import EnvState
+
+
+class LPGTrainState:
+    """flax TrainState of the LPG network: flat params + Adam state (+ the model description)."""
+
+    def __init__(self, model, params, tx, opt_state=None, step=0):
+        self.model, self.params, self.tx = model, params, tx
+        self.opt_state = tx.init(params) if opt_state is None else opt_state
+        self.step = step
+
+    def replace(self, **kw):
+        d = dict(model=self.model, params=self.params, tx=self.tx, opt_state=self.opt_state, step=self.step)
+        d.update(kw)
+        return LPGTrainState(**d)
+
+
+class MetaGradWorkspace:
+    """All device buffers of one meta-gradient step for a chunk of agents (allocated once)."""
+
+    def __init__(self, n_agents, n_workers, rollout_len, obs_dim, num_updates, n_params, device):
+        N, W, L, K = n_agents, n_workers, rollout_len, num_updates
+        R = N * W
+        f32 = torch.float32
+        self.tape = Tape(N, W, L, obs_dim, K, device, keep_gates=True)
+        self.d_pi_hat = torch.empty((L, R), dtype=f32, device=device)
+        self.d_y_hat = torch.empty((L, R, 8), dtype=f32, device=device)
+        self.dl = torch.empty((L, R, 8), dtype=f32, device=device)
+        self.dx = torch.empty((L, R, 2), dtype=f32, device=device)
+        self.lam = torch.empty((N, obs_dim, 8), dtype=f32, device=device)
+        self.mu = torch.empty((N, obs_dim, 8), dtype=f32, device=device)
+        self.whT = torch.empty((768, 256), dtype=f32, device=device)
+        self.partials = torch.empty(_lib.lib().toued_lpg_wgrad_workspace_floats(), dtype=f32, device=device)
+        self.loss_scal = torch.empty((N, 2), dtype=f32, device=device)
+        self.key = (N, W, L, obs_dim, K, n_params, str(device))
+
+
+_WS_CACHE = {}
+
+
+def _workspace(n, w, L, D, K, P, device) -> MetaGradWorkspace:
+    key = (n, w, L, D, K, P, str(device))
+    ws = _WS_CACHE.get(key)
+    if ws is None:
+        _WS_CACHE.clear()
+        ws = _WS_CACHE[key] = MetaGradWorkspace(n, w, L, D, K, P, device)
+    return ws
+
+
+def _world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist
+    return 1, None
+
+
+def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: AgentState, value_critic_states,
+                             rollout_manager, num_mini_batches: int, gamma: float, gae_lambda: float,
+                             lpg_hypers: LpgHyperparams, *, outer_product_quirk: bool = True,
+                             global_agent_offset: int = 0, global_num_agents: Optional[int] = None,
+                             eval_workers: int = 4, return_grad: bool = False):
+    """Update a batch of agents with LPG, then update LPG with the regularised final agent loss
+    (meta/train.py:14-130).  rng: the step key (uint32[2]).  Returns
+    (lpg_train_state, agent_states, value_critic_states, metrics)."""
+    env = rollout_manager.env
+    actor, critic = agent_states.actor_state, agent_states.critic_state
+    N, W = agent_states.env_state.packed.shape
+    L, K, D = rollout_manager.train_rollout_len, lpg_hypers.num_agent_updates, env.obs_dim
+    dev = actor.params.device
+    world, dist = _world()
+    n_global = global_num_agents if global_num_agents is not None else N * world
+    if dist is not None and global_num_agents is None:
+        global_agent_offset = dist.get_rank() * N
+    model = lpg_train_state.model
+    cond = int(model.lifetime_conditioning)
+    lpg = lpg_train_state.params
+    P = lpg.numel()
+    p, s = _lib.ptr, _lib.stream_ptr()
+
+    # ---- keys: split(rng, n_global)[local slice], then the per-agent chain of meta/train.py:40-110
+    rngs = prng.split(np.asarray(rng, np.uint32), n_global)[global_agent_offset:global_agent_offset + N]
+    ks = prng.split(rngs, 2); rngs, r_train = ks[:, 0, :], ks[:, 1, :]
+    ks = prng.split(rngs, 2); rngs, r_eval = ks[:, 0, :], ks[:, 1, :]
+    ks = prng.split(rngs, 2); r_evalagent = ks[:, 1, :]
+
+    if N % num_mini_batches != 0:
+        raise ValueError(f"local agents ({N}) must be divisible by num_mini_batches ({num_mini_batches})")
+    nb = N // num_mini_batches
+    ws = _workspace(nb, W, L, D, K, P, dev)
+    tape = ws.tape
+    gscale = 1.0 / n_global
+    bK = [c / K for c in (lpg_hypers.policy_entropy_coeff, lpg_hypers.target_entropy_coeff,
+                          lpg_hypers.policy_l2_coeff, lpg_hypers.target_l2_coeff)]
+    _lib.call("toued_transpose_wh", p(lpg), p(ws.whT), s)
+
+    new_actor = torch.empty_like(actor.params)
+    new_critic = torch.empty_like(critic.params)
+    new_step = torch.empty_like(actor.step)
+    new_state = torch.empty_like(agent_states.env_state.packed)
+    new_obs = torch.empty_like(agent_states.env_obs)
+    msum = torch.zeros(8, dtype=torch.float32, device=dev)
+    levels_all = agent_states.level.packed
+    returns = torch.empty(N, dtype=torch.float32, device=dev)
+
+    for mb in range(num_mini_batches):
+        sl = slice(mb * nb, (mb + 1) * nb)
+        sub = AgentState(actor.replace(params=actor.params[sl], step=actor.step[sl]),
+                         critic.replace(params=critic.params[sl], step=critic.step[sl]),
+                         _sub_level(agent_states.level, sl), agent_states.env_obs[sl],
+                         EnvState(agent_states.env_state.packed[sl], env.max_n_objs))
+        levels = sub.level.packed
+        # ---- K agent updates (forward, taped) ----
+        sub2, _, am = train_lpg_agent(r_train[sl], lpg_train_state, sub, rollout_manager, K,
+                                      lpg_hypers.agent_target_coeff, tape=tape)
+        # ---- rollout the updated agent (meta/train.py:46-58) ----
+        state = sub2.env_state.packed
+        keys_e = torch.from_numpy(np.ascontiguousarray(r_eval[sl]).view(np.int32)).to(dev, non_blocking=True)
+        _lib.call("toued_rollout", p(levels), p(keys_e), p(tape.actor[K]), None, p(state), p(tape.obs[K]),
+                  p(tape.action[K]), p(tape.reward[K]), p(tape.done[K]), None, nb, W, L, D,
+                  env.max_grid_size, env.max_n_objs, 0, s)
+        _lib.call("toued_sort_tokens", p(tape.obs[K]), p(tape.sorted_tok[K]), nb, W, L, s)
+        # ---- value "update" (Q2) + advantage + LPG loss + lam_K (meta/train.py:60-100) ----
+        vparams = value_critic_states.params[sl]
+        _lib.call("toued_meta_loss", p(tape.obs[K]), p(tape.action[K]), p(tape.reward[K]), p(tape.done[K]),
+                  p(tape.sorted_tok[K]), p(vparams), p(tape.actor[K]), p(ws.lam), p(ws.mu), p(ws.loss_scal),
+                  nb, W, L, D, vparams.shape[-1], float(gamma), float(gae_lambda), float(gscale),
+                  int(outer_product_quirk), s)
+        # ---- reverse pass ----
+        for k in reversed(range(K)):
+            _lib.call("toued_agent_backward", p(tape.obs[k]), p(tape.action[k]), p(tape.sorted_tok[k]),
+                      p(tape.pi_hat[k]), p(tape.y_hat[k]), p(tape.actor[k]), p(tape.critic[k]),
+                      p(tape.actor[k + 1]), p(tape.critic[k + 1]), p(tape.scalars[k]), p(ws.lam), p(ws.mu),
+                      p(ws.d_pi_hat), p(ws.d_y_hat), nb, W, L, D, float(actor.learning_rate),
+                      float(critic.learning_rate), float(actor.max_grad_norm),
+                      float(lpg_hypers.agent_target_coeff), *[float(b) for b in bK], float(gscale), s)
+            _lib.call("toued_gru_backward", p(tape.done[k]), p(lpg), p(ws.whT), p(tape.h[k]), p(tape.gates[k]),
+                      p(tape.y_hat[k]), p(ws.d_pi_hat), p(ws.d_y_hat), p(ws.dl), p(ws.dx), nb, W, L, cond, s)
+            first = (mb == 0 and k == K - 1)
+            _lib.call("toued_lpg_wgrad", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg), p(tape.x[k]),
+                      p(tape.h[k]), p(tape.gates[k]), p(ws.d_pi_hat), p(ws.dl), p(ws.dx), p(ws.partials),
+                      nb, W, L, D, cond, 0 if first else 1, s)
+        # ---- metrics (sums over agents; divided by n_global after the all-reduce) ----
+        lpg_loss, value_loss = ws.loss_scal[:, 0], ws.loss_scal[:, 1]
+        reg = (lpg_loss - lpg_hypers.policy_entropy_coeff * am.policy_entropy + lpg_hypers.policy_l2_coeff * am.policy_l2
+               - lpg_hypers.target_entropy_coeff * am.critic_entropy + lpg_hypers.target_l2_coeff * am.critic_l2)
+        msum[:7] += torch.stack([lpg_loss.sum(), reg.sum(), value_loss.sum(), am.policy_l2.sum(),
+                                 am.policy_entropy.sum(), am.critic_loss.sum(), am.critic_l2.sum()])
+        msum[7] += am.critic_entropy.sum()
+        new_actor[sl] = sub2.actor_state.params
+        new_critic[sl] = sub2.critic_state.params
+        new_step[sl] = sub2.actor_state.step
+        new_state[sl] = state
+        new_obs[sl] = tape.obs[K][:, -1]
+        # ---- evaluate agent return: 4 workers, metric only (meta/train.py:109-117, Q11) ----
+        returns[sl] = eval_agent(r_evalagent[sl], rollout_manager, levels, tape.actor[K], eval_workers)
+
+    grad = torch.empty(P, dtype=torch.float32, device=dev)
+    _lib.call("toued_reduce_partials", p(ws.partials), p(grad), cond, s)
+    mvec = torch.cat([msum, returns.sum().view(1)])
+    if dist is not None:
+        dist.all_reduce(grad)                     # sum of per-rank (1/n_global)-scaled sums = mean
+        dist.all_reduce(mvec)
+    mvec = mvec / n_global
+    # ---- Adam on the LPG parameters (meta/train.py:129) ----
+    new_params = lpg.clone()
+    opt_state = lpg_train_state.tx.update_(new_params, grad, {**lpg_train_state.opt_state,
+                                                              "mu": lpg_train_state.opt_state["mu"].clone(),
+                                                              "nu": lpg_train_state.opt_state["nu"].clone()})
+    new_lpg = lpg_train_state.replace(params=new_params, opt_state=opt_state, step=lpg_train_state.step + 1)
+    agent_out = agent_states.replace(
+        actor_state=actor.replace(params=new_actor, step=new_step),
+        critic_state=critic.replace(params=new_critic, step=new_step.clone()),
+        env_obs=new_obs, env_state=EnvState(new_state, env.max_n_objs))
+    # value critic: parameters untouched (Q2); its step counter advances K + 1 per meta-step
+    value_out = value_critic_states.replace(step=value_critic_states.step + (K + 1))
+    metrics = {
+        "lpg_loss": mvec[0], "reg_lpg_loss": mvec[1], "value_loss": mvec[2],
+        "lpg_agent": {"policy_l2": mvec[3], "policy_entropy": mvec[4], "critic_loss": mvec[5],
+                      "critic_l2": mvec[6], "critic_entropy": mvec[7]},
+        "lpg_agent_return": mvec[8],
+    }
+    if return_grad:
+        metrics["_grad"] = grad
+    return new_lpg, agent_out, value_out, metrics
+
+
+def _sub_level(level, sl):
+    from ..util.data import Level
+    return Level(level.env_params, level.lifetime[sl], level.buffer_id[sl], level.packed[sl])

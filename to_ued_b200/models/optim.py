@@ -1,0 +1,46 @@
+"""Optimisers (reference models/optim.py:5-34).
+
+``create_optimizer("SGD", ...)`` describes optax.chain(clip_by_global_norm, scale(lr), scale(-1));
+for the tabular agents this is fused into toued_agent_update.  ``"Adam"`` is
+optax.chain(scale_by_adam(), scale(lr), scale(-1)) (no clipping on this branch, Q9) and runs in
+toued_adam on the flat LPG parameter vector."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from .. import _lib
+
+
+@dataclass
+class SGD:
+    learning_rate: float
+    max_grad_norm: float
+    name: str = "SGD"
+
+
+class Adam:
+    name = "Adam"
+
+    def __init__(self, learning_rate: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8):
+        self.learning_rate, self.b1, self.b2, self.eps = learning_rate, b1, b2, eps
+
+    def init(self, params: torch.Tensor):
+        return {"mu": torch.zeros_like(params), "nu": torch.zeros_like(params), "count": 0}
+
+    def update_(self, params: torch.Tensor, grad: torch.Tensor, state: dict) -> dict:
+        """In-place Adam step on the GPU; returns the new optimizer state."""
+        count = state["count"] + 1
+        _lib.call("toued_adam", _lib.ptr(params), _lib.ptr(grad), _lib.ptr(state["mu"]), _lib.ptr(state["nu"]),
+                  params.numel(), count, float(self.learning_rate), float(self.b1), float(self.b2), float(self.eps),
+                  _lib.stream_ptr())
+        return {"mu": state["mu"], "nu": state["nu"], "count": count}
+
+
+def create_optimizer(optimizer: str, learning_rate: float, max_grad_norm: float):
+    if optimizer == "SGD":
+        return SGD(learning_rate, max_grad_norm)
+    elif optimizer == "Adam":
+        return Adam(learning_rate)
+    raise ValueError(f"Unknown optimizer: {optimizer}")
