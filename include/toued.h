@@ -141,6 +141,16 @@ int toued_reduce_partials(const float* workspace, float* grad, int lifetime_cond
 int toued_adam(float* params, const float* grad, float* mu, float* nu, int n, int count, float lr,
                float b1, float b2, float eps, void* stream);
 
+/* ---- agent (re-)creation (agents/agents.py:31-95, level_sampler.py:273-291) --------------------- */
+
+/* lecun-normal tables from threefry keys: keys u32[N][2], mask u8[N] or NULL (only masked agents are
+ * written), tables f32[N][D][8] (columns >= n_out zeroed).                                          */
+int toued_init_tables(const uint32_t* keys, const uint8_t* mask, float* tables, int n_agents,
+                      int obs_dim, int n_out, void* stream);
+/* reset the W environments (and the step counter, if given) of every masked agent.                  */
+int toued_masked_reset(const void* levels, const uint8_t* mask, int32_t* state, int32_t* obs,
+                       int32_t* step, int n_agents, int n_workers, int max_grid_size, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,8 @@ SIGNATURES = {
     "toued_lpg_wgrad": [_P] * 11 + [_I] * 6 + [_P],
     "toued_reduce_partials": [_P, _P, _I, _P],
     "toued_adam": [_P] * 4 + [_I, _I] + [_F] * 4 + [_P],
+    "toued_init_tables": [_P] * 3 + [_I] * 3 + [_P],
+    "toued_masked_reset": [_P] * 5 + [_I] * 3 + [_P],
 }
 
 
@@ -79,7 +81,37 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+# kernels launched by one call of each entry point (for the bench's gpu_launches count)
+KERNELS_PER_CALL = {"toued_lpg_wgrad": 3, "toued_init_tables": 2}
+LAUNCHES = {}          # entry point -> number of calls since reset_counters()
+PROFILE = None         # when a dict: entry point -> list of (start, end) CUDA events
+
+
+def reset_counters(profile=False):
+    global PROFILE
+    LAUNCHES.clear()
+    PROFILE = {} if profile else None
+
+
+def kernel_launches():
+    return sum(n * KERNELS_PER_CALL.get(k, 1) for k, n in LAUNCHES.items())
+
+
+def profile_ms():
+    """entry point -> (calls, total ms); call after torch.cuda.synchronize()."""
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (PROFILE or {}).items()}
+
+
 def call(name, *args):
-    rc = getattr(lib(), name)(*args)
+    LAUNCHES[name] = LAUNCHES.get(name, 0) + 1
+    if PROFILE is not None:
+        import torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(lib(), name)(*args)
+        b.record()
+        PROFILE.setdefault(name, []).append((a, b))
+    else:
+        rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise TouedError(f"{name} failed ({rc}): {lib().toued_last_error().decode()}")

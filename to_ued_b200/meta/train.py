@@ -198,7 +198,8 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     agent_out = agent_states.replace(
         actor_state=actor.replace(params=new_actor, step=new_step),
         critic_state=critic.replace(params=new_critic, step=new_step.clone()),
-        env_obs=new_obs, env_state=EnvState(new_state, env.max_n_objs))
+        env_obs=new_obs, env_state=EnvState(new_state, env.max_n_objs),
+        host_step=_advance_host_step(agent_states.host_step, agent_states.level.lifetime, K))
     # value critic: parameters untouched (Q2); its step counter advances K + 1 per meta-step
     value_out = value_critic_states.replace(step=value_critic_states.step + (K + 1))
     metrics = {
@@ -210,6 +211,13 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     if return_grad:
         metrics["_grad"] = grad
     return new_lpg, agent_out, value_out, metrics
+
+
+def _advance_host_step(step, lifetime, k):
+    """K masked updates: step <- step + 1 while step + 1 <= lifetime (lpg_agent.py:78-82)."""
+    if step is None:
+        return None
+    return np.minimum(step + k, np.maximum(step, lifetime)).astype(np.int32)
 
 
 def _sub_level(level, sl):

@@ -24,14 +24,21 @@ def lecun_normal(key, shape, fan_in) -> np.ndarray:
     return (v * (np.sqrt(1.0 / fan_in) / 0.87962566103423978)).astype(np.float32)
 
 
-def init_tables(keys, obs_dim: int, n_out: int, device="cuda") -> torch.Tensor:
-    """One lecun-normal table per key: keys uint32[N, 2] -> f32[N, D, 8] on ``device``."""
-    keys = np.asarray(keys, np.uint32).reshape(-1, 2)
-    w = lecun_normal(keys, (obs_dim, n_out), obs_dim)              # [N, D, C]
-    out = np.zeros((keys.shape[0], obs_dim, TABLE_PAD), np.float32)
-    out[..., :n_out] = w
-    t = torch.from_numpy(out)
-    return t.to(device) if device != "cpu" else t
+def init_tables(keys, obs_dim: int, n_out: int, device="cuda", out=None, mask=None) -> torch.Tensor:
+    """One lecun-normal table per key: keys uint32[N, 2] -> f32[N, D, 8] on the GPU (toued_init_tables;
+    same draw as ``lecun_normal`` above up to erfinv rounding).  ``out`` / ``mask`` re-initialise only the
+    masked agents of an existing tensor."""
+    from .. import _lib
+    keys = np.ascontiguousarray(np.asarray(keys, np.uint32).reshape(-1, 2))
+    n = keys.shape[0]
+    kd = torch.from_numpy(keys.view(np.int32)).to(device, non_blocking=True)
+    if out is None:
+        out = torch.empty((n, obs_dim, TABLE_PAD), dtype=torch.float32, device=device)
+    md = None
+    if mask is not None:
+        md = mask if isinstance(mask, torch.Tensor) else torch.from_numpy(np.asarray(mask, np.uint8)).to(device, non_blocking=True)
+    _lib.call("toued_init_tables", _lib.ptr(kd), _lib.ptr(md), _lib.ptr(out), n, obs_dim, n_out, _lib.stream_ptr())
+    return out
 
 
 class Actor:

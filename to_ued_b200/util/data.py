@@ -87,6 +87,7 @@ class AgentState:
     level: Level
     env_obs: torch.Tensor           # int32 [N, W] packed observation
     env_state: Any                  # EnvState ([N, W] packed)
+    host_step: Optional[np.ndarray] = None   # host mirror of actor_state.step (deterministic evolution)
 
     def replace(self, **kw):
         return _replace(self, **kw)
