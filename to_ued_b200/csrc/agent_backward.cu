@@ -359,10 +359,8 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
 #pragma unroll
     for (int j = 0; j < 13; ++j) wl[j] = s_wlast[j];
 
-    // ---- B3. per row segment: w_row, then per token: cotangents + Hessian-vector product -------
-    float hl[13];
-#pragma unroll
-    for (int j = 0; j < 13; ++j) hl[j] = 0.f;
+    // ---- B3a. per row segment: w_row = k * (lam_row - proj * g_row), broadcast into the records of
+    //           the segment's tokens (their forward-gradient records are no longer needed) ----------
     for (int i = tid; i < T; i += 256) {
         if (!seg_head(st, ob, i)) continue;
         const int row = ob_idx(ob[st[i]]);
@@ -376,72 +374,95 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
 #pragma unroll
             for (int j = 0; j < 13; ++j) g[j] += rec[tk * 14 + j];
         }
-        float l8[8], m8[8], wr[13], hr[13];
+        float l8[8], m8[8], wr[13];
         load8(lm + (size_t)row * 8, l8); load8(mm + (size_t)row * 8, m8);
 #pragma unroll
         for (int j = 0; j < 5; ++j) wr[j] = ka * (l8[j] - pa_ * g[j]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) wr[5 + j] = kc * (m8[j] - pc_ * g[5 + j]);
-#pragma unroll
-        for (int j = 0; j < 13; ++j) hr[j] = 0.f;
         for (int q = i; q < qe; ++q) {
-            const int tok = st[q];
-            const int t = tok / W, w = tok - t * W;
-            const size_t li = (size_t)t * R + (size_t)n * W + w;
-            const TokFwd f = tok_forward(a0, c0, D, ob[tok], act[tok]);
-            const float ph = pi_hat[li];
-            float yh[8]; load8(y_hat + li * 8, yh);
-            float v[13];
+            float* r = rec + st[q] * 14;
 #pragma unroll
-            for (int j = 0; j < 13; ++j) v[j] = fmaf(f.tf, wl[j], wr[j]);
-            // actor:  S = q * (v_a - p.v)
-            float va = v[0], pv = 0.f;
+            for (int j = 0; j < 13; ++j) r[j] = wr[j];
+        }
+    }
+    __syncthreads();
+    // ---- B3b. token-parallel: cotangents of pi_hat / y_hat and the Hessian-vector contributions ----
+    float hl[13];
 #pragma unroll
-            for (int j = 1; j < 5; ++j) va = (f.a == j) ? v[j] : va;
+    for (int j = 0; j < 13; ++j) hl[j] = 0.f;
+    for (int tok = tid; tok < T; tok += 256) {
+        const int t = tok / W, w = tok - t * W;
+        const size_t li = (size_t)t * R + (size_t)n * W + w;
+        const TokFwd f = tok_forward(a0, c0, D, ob[tok], act[tok]);
+        const float ph = pi_hat[li];
+        float yh[8]; load8(y_hat + li * 8, yh);
+        float* r = rec + tok * 14;
+        float v[13];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) pv = fmaf(f.p[j], v[j], pv);
-            const float s = va - pv;
-            d_pi_hat[li] = invT * f.q * s + dir_pi * ph;
-            const float pe = f.pa + 1e-8f;
-            const float c1_ = ph * invT * s * 1e-8f * f.pa / (pe * pe), c2_ = ph * invT * f.q;
-            float h[13];
+        for (int j = 0; j < 13; ++j) v[j] = fmaf(f.tf, wl[j], r[j]);
+        // actor:  S = q * (v_a - p.v)
+        float va = v[0], pv = 0.f;
 #pragma unroll
-            for (int j = 0; j < 5; ++j)
-                h[j] = c1_ * ((f.a == j ? 1.0f : 0.0f) - f.p[j]) - c2_ * f.p[j] * (v[j] - pv);
-            // critic:  S = sum_i v_i y_i m_i - (v.y)(y.m)
-            float m[8], mp[8], av = 0.f, b = 0.f;
+        for (int j = 1; j < 5; ++j) va = (f.a == j) ? v[j] : va;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float ye = f.y[j] + 1e-8f;
-                m[j] = logf(ye) - logf(yh[j] + 1e-8f) + f.y[j] / ye;
-                mp[j] = (f.y[j] + 2e-8f) / (ye * ye);
-                av = fmaf(v[5 + j], f.y[j], av);
-                b = fmaf(f.y[j], m[j], b);
-            }
-            const float ca = alpha * invT;
-            float dS[8], sy = 0.f, dyo[8];
+        for (int j = 0; j < 5; ++j) pv = fmaf(f.p[j], v[j], pv);
+        const float s = va - pv;
+        d_pi_hat[li] = invT * f.q * s + dir_pi * ph;
+        const float pe = f.pa + 1e-8f;
+        const float c1_ = ph * invT * s * 1e-8f * f.pa / (pe * pe), c2_ = ph * invT * f.q;
+        float h[13];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float vc = v[5 + j];
-                dyo[j] = ca * f.y[j] * (av - vc) / (yh[j] + 1e-8f) + dir_y * yh[j];
-                dS[j] = vc * m[j] + vc * f.y[j] * mp[j] - vc * b - av * (m[j] + f.y[j] * mp[j]);
-                sy = fmaf(f.y[j], dS[j], sy);
-            }
+        for (int j = 0; j < 5; ++j)
+            h[j] = c1_ * ((f.a == j ? 1.0f : 0.0f) - f.p[j]) - c2_ * f.p[j] * (v[j] - pv);
+        // critic:  S = sum_i v_i y_i m_i - (v.y)(y.m)
+        float m[8], mp[8], av = 0.f, b = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) h[5 + j] = ca * f.y[j] * (dS[j] - sy);
-            float4* o = reinterpret_cast<float4*>(d_y_hat + li * 8);
-            o[0] = make_float4(dyo[0], dyo[1], dyo[2], dyo[3]);
-            o[1] = make_float4(dyo[4], dyo[5], dyo[6], dyo[7]);
+        for (int j = 0; j < 8; ++j) {
+            const float ye = f.y[j] + 1e-8f;
+            m[j] = logf(ye) - logf(yh[j] + 1e-8f) + f.y[j] / ye;
+            mp[j] = (f.y[j] + 2e-8f) / (ye * ye);
+            av = fmaf(v[5 + j], f.y[j], av);
+            b = fmaf(f.y[j], m[j], b);
+        }
+        const float ca = alpha * invT;
+        float dS[8], sy = 0.f, dyo[8];
 #pragma unroll
-            for (int j = 0; j < 13; ++j) { hr[j] += h[j]; hl[j] = fmaf(f.tf, h[j], hl[j]); }
+        for (int j = 0; j < 8; ++j) {
+            const float vc = v[5 + j];
+            dyo[j] = ca * f.y[j] * (av - vc) / (yh[j] + 1e-8f) + dir_y * yh[j];
+            dS[j] = vc * m[j] + vc * f.y[j] * mp[j] - vc * b - av * (m[j] + f.y[j] * mp[j]);
+            sy = fmaf(f.y[j], dS[j], sy);
         }
 #pragma unroll
-        for (int j = 0; j < 5; ++j) lm[(size_t)row * 8 + j] = l8[j] + hr[j];
+        for (int j = 0; j < 8; ++j) h[5 + j] = ca * f.y[j] * (dS[j] - sy);
+        float4* o = reinterpret_cast<float4*>(d_y_hat + li * 8);
+        o[0] = make_float4(dyo[0], dyo[1], dyo[2], dyo[3]);
+        o[1] = make_float4(dyo[4], dyo[5], dyo[6], dyo[7]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) mm[(size_t)row * 8 + j] = m8[j] + hr[5 + j];
+        for (int j = 0; j < 13; ++j) { r[j] = h[j]; hl[j] = fmaf(f.tf, h[j], hl[j]); }
     }
 #pragma unroll
     for (int j = 0; j < 13; ++j) hl[j] = block_sum(hl[j], red);
+    __syncthreads();
+    // ---- B3c. segmented sums of the HVP contributions into lam_k / mu_k --------------------------
+    for (int i = tid; i < T; i += 256) {
+        if (!seg_head(st, ob, i)) continue;
+        const int row = ob_idx(ob[st[i]]);
+        float hr[13];
+#pragma unroll
+        for (int j = 0; j < 13; ++j) hr[j] = 0.f;
+        for (int q = i; q < T; ++q) {
+            const int tk = st[q];
+            if (ob_idx(ob[tk]) != row) break;
+#pragma unroll
+            for (int j = 0; j < 13; ++j) hr[j] += rec[tk * 14 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) lm[(size_t)row * 8 + j] += hr[j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mm[(size_t)row * 8 + j] += hr[5 + j];
+    }
     if (tid == 0) {
 #pragma unroll
         for (int j = 0; j < 5; ++j) lm[(size_t)(D - 1) * 8 + j] = ll[j] + hl[j];
