@@ -151,6 +151,22 @@ int toued_init_tables(const uint32_t* keys, const uint8_t* mask, float* tables, 
 int toued_masked_reset(const void* levels, const uint8_t* mask, int32_t* state, int32_t* obs,
                        int32_t* step, int n_agents, int n_workers, int max_grid_size, void* stream);
 
+/* ---- tensor-core (tcgen05 / TMEM) path -------------------------------------------------------- */
+
+/* Unit check of the tcgen05 building blocks: D f32[128][48] = A f32[128][256] * B f32[48][256]^T with
+ * fp16 operands / fp32 accumulation in TMEM.  scratch_img: 24 KiB device scratch.                  */
+int toued_tc_gemm_test(const float* A, const float* B, void* scratch_img, float* D, void* stream);
+
+/* Pack the recurrent matrix Wh into the fp16 SW128 pass images the tensor-core forward streams
+ * (wh_img: 384 KiB, once per meta-step).                                                           */
+int toued_pack_wh_forward(const float* lpg_params, void* wh_img, void* stream);
+/* Tensor-core version of toued_gru_forward (models/lpg.py:11-30,77-84): fp16 operands, fp32
+ * accumulation in TMEM.  h16 f16[L][R][256] and g16 f16[4][L][R][256] (r, z, n, Whn h + bhn) are
+ * saved in half precision for the reverse pass; pi_hat / y_hat stay fp32.                          */
+int toued_gru_forward_tc(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,
+                         void* h16, void* g16, float* pi_hat, float* y_hat, int n_agents, int n_workers,
+                         int rollout_len, int lifetime_conditioning, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

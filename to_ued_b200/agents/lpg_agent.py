@@ -36,7 +36,8 @@ class LPGAgentMetrics:
 class Tape:
     """Saved-for-backward buffers of K agent updates (all on the GPU, allocated once and reused)."""
 
-    def __init__(self, n_agents, n_workers, rollout_len, obs_dim, num_updates, device, keep_gates=True):
+    def __init__(self, n_agents, n_workers, rollout_len, obs_dim, num_updates, device, keep_gates=True,
+                 precision=None):
         N, W, L, D, K = n_agents, n_workers, rollout_len, obs_dim, num_updates
         R, dev = N * W, device
         f32, u8, i32 = torch.float32, torch.uint8, torch.int32
@@ -49,9 +50,20 @@ class Tape:
         self.reward = torch.empty((K + 1, N, L, W), dtype=f32, device=dev)
         self.done = torch.empty((K + 1, N, L, W), dtype=u8, device=dev)
         self.sorted_tok = torch.empty((K + 1, N, L * W), dtype=torch.int16, device=dev)
+        import to_ued_b200
+        self.precision = precision or to_ued_b200.GRU_PRECISION
         self.x = torch.empty((K, L, R, 8), dtype=f32, device=dev)
-        self.h = torch.empty((K, L, R, 256), dtype=f32, device=dev)
-        self.gates = torch.empty((K, 4, L, R, 256), dtype=f32, device=dev) if keep_gates else None
+        if self.precision == "tc":
+            f16 = torch.float16
+            kk = K if keep_gates else 1                      # without a reverse pass one slot is enough
+            self.h16 = torch.empty((kk, L, R, 256), dtype=f16, device=dev)
+            self.g16 = torch.empty((kk, 4, L, R, 256), dtype=f16, device=dev)
+            self.wh_img = torch.empty(256 * 768, dtype=f16, device=dev)
+            self.wh_img_version = None
+            self.h = self.gates = None
+        else:
+            self.h = torch.empty((K, L, R, 256), dtype=f32, device=dev)
+            self.gates = torch.empty((K, 4, L, R, 256), dtype=f32, device=dev) if keep_gates else None
         self.pi_hat = torch.empty((K, L, R), dtype=f32, device=dev)
         self.y_hat = torch.empty((K, L, R, 8), dtype=f32, device=dev)
         self.scalars = torch.empty((K, N, 8), dtype=f32, device=dev)
@@ -74,9 +86,15 @@ def lpg_agent_train_step(k, tape: Tape, levels, step, lpg_params, lifetime_condi
     _lib.call("toued_lpg_prepare", p(tape.obs[k]), p(tape.action[k]), p(tape.reward[k]), p(tape.done[k]),
               p(tape.actor[k]), p(tape.critic[k]), p(lpg_params), p(step), p(levels), p(tape.x[k]),
               N, W, L, D, int(lifetime_conditioning), s)
-    _lib.call("toued_gru_forward", p(tape.x[k]), p(tape.done[k]), p(lpg_params), p(tape.h[k]),
-              p(tape.gates[k]) if tape.gates is not None else None, p(tape.pi_hat[k]), p(tape.y_hat[k]),
-              N, W, L, int(lifetime_conditioning), s)
+    if tape.precision == "tc":
+        ks = k % tape.h16.shape[0]
+        _lib.call("toued_gru_forward_tc", p(tape.x[k]), p(tape.done[k]), p(lpg_params), p(tape.wh_img),
+                  p(tape.h16[ks]), p(tape.g16[ks]), p(tape.pi_hat[k]), p(tape.y_hat[k]),
+                  N, W, L, int(lifetime_conditioning), s)
+    else:
+        _lib.call("toued_gru_forward", p(tape.x[k]), p(tape.done[k]), p(lpg_params), p(tape.h[k]),
+                  p(tape.gates[k]) if tape.gates is not None else None, p(tape.pi_hat[k]), p(tape.y_hat[k]),
+                  N, W, L, int(lifetime_conditioning), s)
     _lib.call("toued_agent_update", p(tape.obs[k]), p(tape.action[k]), p(tape.sorted_tok[k]), p(tape.pi_hat[k]),
               p(tape.y_hat[k]), p(tape.actor[k]), p(tape.critic[k]), p(tape.actor[k + 1]), p(tape.critic[k + 1]),
               p(levels), p(step), p(tape.scalars[k]), N, W, L, D, float(lr_actor), float(lr_critic),
@@ -109,6 +127,8 @@ def train_lpg_agent(rng, lpg_train_state, agent_state: AgentState, rollout_manag
     p = _lib.ptr
     lpg = lpg_train_state.params if hasattr(lpg_train_state, "params") else lpg_train_state
     cond = lpg_train_state.model.lifetime_conditioning if hasattr(lpg_train_state, "model") else (lpg.numel() > 204000)
+    if tape.precision == "tc":                                # recurrent matrix -> fp16 SW128 pass images
+        _lib.call("toued_pack_wh_forward", p(lpg), p(tape.wh_img), s)
     for k in range(K):
         _lib.call("toued_rollout", p(levels), p(keys_d[k]), p(tape.actor[k]), None, p(state), p(tape.obs[k]),
                   p(tape.action[k]), p(tape.reward[k]), p(tape.done[k]), None, N, W, L, env.obs_dim,

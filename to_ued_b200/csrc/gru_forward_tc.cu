@@ -1,0 +1,276 @@
+// Tensor-core GRU forward (tcgen05 / TMEM / TMA), the production path for models/lpg.py:11-30,77-84.
+//
+// A CTA owns 128 sequences (UMMA_M = 128, cta_group::1) for all L reverse-scan steps.
+//   * hidden state h' lives in shared memory as the fp16 K-major SW128 A operand (4 K-blocks x 16 KB),
+//     double-buffered: MMAs of step t read A[cur] while the epilogue writes h_t into A[nxt];
+//   * the recurrent matrix is pre-packed once per meta-step into fp16 SW128 "pass" images
+//     (16 passes x [3 gates x 16 units = 48 rows][256 k] = 24 KB each) and streamed from L2 by a
+//     TMA-producer warp (cp.async.bulk + mbarrier, 2 stages);
+//   * one elected thread issues tcgen05.mma (M128 N48 K16, 16 per pass) into a double-buffered TMEM
+//     accumulator and commits to mbarriers;
+//   * 8 epilogue warps tcgen05.ld the three gate pre-activations of their (row, 8 units), add the fp32
+//     input projection x W_i + b_i, apply the flax GRUCell gate math, write h_t (fp16) into A[nxt] and
+//     h / r / z / n / (W_hn h + b_hn) (fp16) to HBM for the reverse pass, and accumulate the two heads
+//     (pi_hat, y_hat logits) on relu(h_t) in registers.
+// fp16 operands / fp32 accumulate: the hidden state is quantised to fp16 once per step (|h| < 1).
+// Parity is checked against the exact-fp32 SIMT kernel and the fp64 oracle with a stated tolerance.
+#include "tc.cuh"
+#include "lpg_common.cuh"
+#include "../../include/toued.h"
+
+constexpr int FT_M = 128;                 // rows per CTA
+constexpr int FT_PU = 16;                 // hidden units per pass
+constexpr int FT_PN = 3 * FT_PU;          // 48 accumulator columns per pass
+constexpr int FT_NPASS = LPG_H / FT_PU;   // 16
+constexpr int FT_KB = LPG_H / 64;         // 4 K-blocks
+constexpr int FT_BSTAGE = FT_KB * FT_PN * 128;     // 24576 B per pass image
+constexpr int FT_ABUF = FT_KB * FT_M * 128;        // 65536 B
+constexpr int FT_NS = 2;                  // B stages
+constexpr int FT_THREADS = 320;           // 8 epilogue warps + producer warp + MMA warp
+
+// Wh[k][c] (fp32, c = g*256 + unit) -> fp16 pass images: image[p][kb][row = g*16 + u][128 B swizzled]
+__global__ void pack_wh_fwd_kernel(const float* __restrict__ Wh, __half* __restrict__ img) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= LPG_H * LPG_G) return;
+    const int k = i / LPG_G, c = i % LPG_G;
+    const int g = c / LPG_H, unit = c % LPG_H, p = unit / FT_PU, u = unit % FT_PU;
+    char* base = reinterpret_cast<char*>(img) + (size_t)p * FT_BSTAGE;
+    *reinterpret_cast<__half*>(base + sw128_offset(FT_PN, g * FT_PU + u, k)) = __float2half_rn(Wh[i]);
+}
+
+extern "C" int toued_pack_wh_forward(const float* lpg_params, void* wh_img, void* stream) {
+    pack_wh_fwd_kernel<<<(LPG_H * LPG_G + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        lpg_params + lpg_offsets(5).Wh, (__half*)wh_img);
+    TOUED_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int X>
+__global__ void __launch_bounds__(FT_THREADS, 1)
+gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ done,
+                      const float* __restrict__ lpg, const __half* __restrict__ wh_img,
+                      __half* __restrict__ h16, __half* __restrict__ g16, float* __restrict__ pi_hat,
+                      float* __restrict__ y_hat, int R, int L, int W) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sA = smem;                                   // 2 x 64 KB
+    unsigned char* sB = sA + 2 * FT_ABUF;                       // FT_NS x 24 KB
+    float* sWi = reinterpret_cast<float*>(sB + FT_NS * FT_BSTAGE);   // [X][768]
+    float* sbi = sWi + X * LPG_G;                               // [768]
+    float* sbhn = sbi + LPG_G;                                  // [256]
+    float* swp = sbhn + LPG_H;                                  // [256]
+    float* sWy = swp + LPG_H;                                   // [256][8]
+    float* shead = sWy + LPG_H * LPG_Y;                         // [128][9] partial heads of the hf=1 half
+    __shared__ __align__(8) uint64_t b_full[FT_NS], b_empty[FT_NS], acc_full[2], acc_empty[2], a_ready;
+    __shared__ uint32_t tmem_base_s;
+
+    const LpgOffsets o = lpg_offsets(X);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * FT_M;
+
+    if (tid == 0) {
+        for (int s = 0; s < FT_NS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
+        mbar_init(&a_ready, 8);
+        mbar_fence_init();
+    }
+    if (warp == 9) tmem_alloc(&tmem_base_s, 128);
+    for (int i = tid; i < X * LPG_G; i += FT_THREADS) sWi[i] = lpg[o.Wi + i];
+    for (int i = tid; i < LPG_G; i += FT_THREADS) sbi[i] = lpg[o.bi + i];
+    for (int i = tid; i < LPG_H; i += FT_THREADS) { sbhn[i] = lpg[o.bhn + i]; swp[i] = lpg[o.w_pi + i]; }
+    for (int i = tid; i < LPG_H * LPG_Y; i += FT_THREADS) sWy[i] = lpg[o.W_y + i];
+    // initial carry = 0 (both A buffers)
+    for (int i = tid; i < 2 * FT_ABUF / 16; i += FT_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 8) {
+        // ===================== TMA producer: stream the 16 pass images per step =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = L - 1; t >= 0; --t) {
+                for (int p = 0; p < FT_NPASS; ++p, ++it) {
+                    const int s = it % FT_NS;
+                    mbar_wait(&b_empty[s], ((it / FT_NS) & 1) ^ 1);
+                    mbar_expect_tx(&b_full[s], FT_BSTAGE);
+                    bulk_g2s(sB + s * FT_BSTAGE, reinterpret_cast<const char*>(wh_img) + (size_t)p * FT_BSTAGE,
+                             FT_BSTAGE, &b_full[s]);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer ==========================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc(FT_M, FT_PN, 0);
+            uint32_t it = 0;
+            int cur = 0;
+            for (int t = L - 1, step = 0; t >= 0; --t, ++step) {
+                if (step > 0) { mbar_wait(&a_ready, (step - 1) & 1); }
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + cur * FT_ABUF);
+                for (int p = 0; p < FT_NPASS; ++p, ++it) {
+                    const int s = it % FT_NS, a = it & 1;
+                    mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+                    mbar_wait(&b_full[s], (it / FT_NS) & 1);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(sB + s * FT_BSTAGE);
+                    const uint32_t d_addr = tmem_base + a * 64;
+#pragma unroll
+                    for (int kb = 0; kb < FT_KB; ++kb) {
+                        const uint64_t ad = tc_smem_desc(a_addr + kb * FT_M * 128);
+                        const uint64_t bd = tc_smem_desc(b_addr + kb * FT_PN * 128);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) tc_mma(d_addr, ad + 2 * ks, bd + 2 * ks, idesc, (kb | ks) != 0);
+                    }
+                    tc_commit(&b_empty[s]);
+                    tc_commit(&acc_full[a]);
+                }
+                cur ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue warps 0..7 ===================================================
+        const int q = warp & 3, hf = warp >> 2;
+        const int rl = q * 32 + lane;                 // row within the tile == TMEM lane
+        const int row = row0 + rl;
+        const bool rv = row < R;
+        const int rsafe = rv ? row : 0;
+        const int n_ag = rsafe / W, w_ag = rsafe % W;
+        const size_t gs = (size_t)L * R * LPG_H;
+        uint32_t it = 0;
+        int cur = 0;
+        for (int t = L - 1; t >= 0; --t) {
+            float xr[X];
+            {
+                const float4* xp = reinterpret_cast<const float4*>(x + ((size_t)t * R + rsafe) * LPG_XP);
+                const float4 x0 = xp[0], x1 = xp[1];
+                const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int i = 0; i < X; ++i) xr[i] = rv ? xa[i] : 0.0f;
+            }
+            // mask for the NEXT processed step (t-1): its carry is zero where done[t-1]
+            const bool zero_next = (t > 0) && done[((size_t)n_ag * L + (t - 1)) * W + w_ag];
+            const unsigned char* Acur = sA + cur * FT_ABUF;
+            unsigned char* Anxt = sA + (cur ^ 1) * FT_ABUF;
+            float head[1 + LPG_Y];
+#pragma unroll
+            for (int c = 0; c < 1 + LPG_Y; ++c) head[c] = 0.0f;
+            const size_t tokbase = ((size_t)t * R + rsafe) * LPG_H;
+            for (int p = 0; p < FT_NPASS; ++p, ++it) {
+                const int a = it & 1;
+                mbar_wait(&acc_full[a], (it >> 1) & 1);
+                tc_fence_after();
+                float ar[8], az[8], an[8];
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a * 64 + hf * 8;
+                tmem_ld8(ta, ar);
+                tmem_ld8(ta + FT_PU, az);
+                tmem_ld8(ta + 2 * FT_PU, an);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[a]);
+                const int u0 = p * FT_PU + hf * 8;              // first of this thread's 8 units
+                const uint32_t soff = sw128_offset(FT_M, rl, u0);
+                const uint4 hp_raw = *reinterpret_cast<const uint4*>(Acur + soff);
+                const __half2* hp2 = reinterpret_cast<const __half2*>(&hp_raw);
+                float hp[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hp2[e]); hp[2 * e] = f.x; hp[2 * e + 1] = f.y; }
+                float hv[8], rr[8], zz[8], nn[8], hn[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int u = u0 + e;
+                    float gr = sbi[u], gz = sbi[LPG_H + u], gn = sbi[2 * LPG_H + u];
+#pragma unroll
+                    for (int i = 0; i < X; ++i) {
+                        gr = fmaf(xr[i], sWi[i * LPG_G + u], gr);
+                        gz = fmaf(xr[i], sWi[i * LPG_G + LPG_H + u], gz);
+                        gn = fmaf(xr[i], sWi[i * LPG_G + 2 * LPG_H + u], gn);
+                    }
+                    rr[e] = sigmoidf_(gr + ar[e]);
+                    zz[e] = sigmoidf_(gz + az[e]);
+                    hn[e] = an[e] + sbhn[u];
+                    nn[e] = tanhf_(gn + rr[e] * hn[e]);
+                    hv[e] = (1.0f - zz[e]) * nn[e] + zz[e] * hp[e];
+                    const float y = fmaxf(hv[e], 0.0f);
+                    head[0] = fmaf(y, swp[u], head[0]);
+#pragma unroll
+                    for (int c = 0; c < LPG_Y; ++c) head[1 + c] = fmaf(y, sWy[u * LPG_Y + c], head[1 + c]);
+                }
+                auto pack8 = [](const float (&v)[8]) {
+                    uint4 r;
+                    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+                    __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+                    r.x = *reinterpret_cast<uint32_t*>(&h0); r.y = *reinterpret_cast<uint32_t*>(&h1);
+                    r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
+                    return r;
+                };
+                const uint4 hpk = pack8(hv);
+                *reinterpret_cast<uint4*>(Anxt + soff) = zero_next ? make_uint4(0u, 0u, 0u, 0u) : hpk;
+                if (rv) {
+                    *reinterpret_cast<uint4*>(h16 + tokbase + u0) = hpk;
+                    *reinterpret_cast<uint4*>(g16 + tokbase + u0) = pack8(rr);
+                    *reinterpret_cast<uint4*>(g16 + gs + tokbase + u0) = pack8(zz);
+                    *reinterpret_cast<uint4*>(g16 + 2 * gs + tokbase + u0) = pack8(nn);
+                    *reinterpret_cast<uint4*>(g16 + 3 * gs + tokbase + u0) = pack8(hn);
+                }
+            }
+            // A[nxt] complete for this thread: make it visible to the async proxy, signal the MMA warp
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_ready);
+            // heads: combine the two unit-halves of each row (hf = 1 -> smem -> hf = 0)
+            if (hf == 1) {
+#pragma unroll
+                for (int c = 0; c < 1 + LPG_Y; ++c) shead[rl * 9 + c] = head[c];
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");          // epilogue warps only
+            if (hf == 0 && rv) {
+                const float b_pi = lpg[o.b_pi];
+                float zl[LPG_Y], pr[LPG_Y];
+#pragma unroll
+                for (int c = 0; c < LPG_Y; ++c) zl[c] = head[1 + c] + shead[rl * 9 + 1 + c] + lpg[o.b_y + c];
+                softmax_c<LPG_Y>(zl, pr);
+                const size_t tok = (size_t)t * R + row;
+                pi_hat[tok] = head[0] + shead[rl * 9] + b_pi;
+                float4* yo = reinterpret_cast<float4*>(y_hat + tok * LPG_Y);
+                yo[0] = make_float4(pr[0], pr[1], pr[2], pr[3]);
+                yo[1] = make_float4(pr[4], pr[5], pr[6], pr[7]);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            cur ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem_base, 128);
+}
+
+static size_t gru_fwd_tc_smem(int X) {
+    return 2 * FT_ABUF + FT_NS * FT_BSTAGE + sizeof(float) * (X * LPG_G + LPG_G + 2 * LPG_H + LPG_H * LPG_Y + FT_M * 9) + 1024;
+}
+
+extern "C" int toued_gru_forward_tc(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,
+                                    void* h16, void* g16, float* pi_hat, float* y_hat, int n_agents, int n_workers,
+                                    int rollout_len, int lifetime_conditioning, void* stream) {
+    const int R = n_agents * n_workers;
+    TOUED_CHECK(R > 0 && rollout_len > 0, "toued_gru_forward_tc: empty problem");
+    const int blocks = (R + FT_M - 1) / FT_M;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (lifetime_conditioning) {
+        const size_t smem = gru_fwd_tc_smem(7);
+        TOUED_CUDA(cudaFuncSetAttribute(gru_forward_tc_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gru_forward_tc_kernel<7><<<blocks, FT_THREADS, smem, st>>>(x, done, lpg_params, (const __half*)wh_img, (__half*)h16,
+                                                                    (__half*)g16, pi_hat, y_hat, R, rollout_len, n_workers);
+    } else {
+        const size_t smem = gru_fwd_tc_smem(5);
+        TOUED_CUDA(cudaFuncSetAttribute(gru_forward_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gru_forward_tc_kernel<5><<<blocks, FT_THREADS, smem, st>>>(x, done, lpg_params, (const __half*)wh_img, (__half*)h16,
+                                                                    (__half*)g16, pi_hat, y_hat, R, rollout_len, n_workers);
+    }
+    TOUED_LAUNCH_CHECK();
+    return 0;
+}

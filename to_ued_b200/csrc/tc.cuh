@@ -1,0 +1,67 @@
+// tcgen05 / TMEM / mbarrier helpers (sm_100a inline PTX).
+//
+// Operand convention used by every tensor-core kernel here: both operands K-major fp16/bf16 in shared
+// memory as "SW128 K-block tiles": a K-block is 64 elements (128 B) wide; row r of a K-block occupies
+// bytes [r*128, r*128+128) and its 16-byte chunk c is stored at chunk position c ^ (r & 7)
+// (the 128-byte swizzle, Swizzle<3,4,3>).  Tiles are 1024-byte aligned; groups of 8 rows are 1024 B
+// apart (SBO).  Matches cute::UMMA K-major SWIZZLE_128B canonical layout
+// ((8,n),2):((8,SBO),1) in 16-byte units (descriptor fields: version=1, LBO=1, SBO=64, layout=2).
+#pragma once
+#include "common.cuh"
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+constexpr int TC_KB_ELEMS = 64;        // elements per K-block (128 B of fp16/bf16)
+constexpr int TC_UMMA_K = 16;          // K per tcgen05.mma for 16-bit inputs
+
+// byte offset of element (row, k) inside a K-major SW128 tile set whose K-blocks are `rows*128` B apart
+__host__ __device__ __forceinline__ uint32_t sw128_offset(int rows, int row, int k) {
+    const int kb = k >> 6, kin = k & 63;
+    const int chunk = kin >> 3;
+    return (uint32_t)kb * (uint32_t)rows * 128u + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4) +
+           (uint32_t)((kin & 7) << 1);
+}
+
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor, kind::f16, fp32 accumulate, both operands K-major. fmt: 0 = f16, 1 = bf16
+__host__ __device__ constexpr uint32_t tc_idesc(int M, int N, int fmt) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// TMEM allocation: executed by ONE full warp; column count a power of two >= 32
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// 32 lanes x 8 consecutive columns: thread i of the warp gets row (lane quadrant base + i)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}

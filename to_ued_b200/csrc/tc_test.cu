@@ -1,0 +1,82 @@
+// Unit kernel for the tcgen05 building blocks: D[128][N] = A[128][K] * B[N][K]^T with fp16 operands
+// (fp32 in global, converted on the fly), K = 256, N = 48 — the tile shape the GRU kernels use.
+// Exercises: SW128 K-major operand tiles, smem/instruction descriptors, cp.async.bulk of a pre-swizzled
+// B image, tcgen05.mma accumulation in TMEM, tcgen05.commit -> mbarrier, tcgen05.ld.
+#include "tc.cuh"
+#include "../../include/toued.h"
+
+// B[N][K] fp32 (row-major) -> fp16 SW128 image: K-block kb at byte kb*N*128
+__global__ void pack_b_sw128_kernel(const float* __restrict__ B, __half* __restrict__ img, int N, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * K) return;
+    const int n = i / K, k = i % K;
+    *reinterpret_cast<__half*>(reinterpret_cast<char*>(img) + sw128_offset(N, n, k)) = __float2half_rn(B[i]);
+}
+
+template <int N, int K>
+__global__ void __launch_bounds__(128, 1)
+tc_gemm_test_kernel(const float* __restrict__ A, const __half* __restrict__ Bimg, float* __restrict__ D) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sA = smem;                              // K/64 K-blocks x 128 rows x 128 B
+    unsigned char* sB = smem + (K / 64) * 128 * 128;       // K/64 K-blocks x N rows x 128 B
+    __shared__ __align__(8) uint64_t bar_b, bar_mma;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc(&tmem_base, 64);
+    if (tid == 0) { mbar_init(&bar_b, 1); mbar_init(&bar_mma, 1); mbar_fence_init(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tmem_base;
+    if (tid == 0) {
+        mbar_expect_tx(&bar_b, (K / 64) * N * 128);
+        bulk_g2s(sB, Bimg, (K / 64) * N * 128, &bar_b);
+    }
+    // A: row = tid, convert fp32 -> fp16 into the swizzled tile
+    for (int k = 0; k < K; k += 8) {
+        __half2 h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(A[tid * K + k + 2 * e], A[tid * K + k + 2 * e + 1]);
+        *reinterpret_cast<uint4*>(sA + sw128_offset(128, tid, k)) = *reinterpret_cast<uint4*>(h);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        mbar_wait(&bar_b, 0);
+        tc_fence_after();
+        constexpr uint32_t idesc = tc_idesc(128, N, 0);
+#pragma unroll
+        for (int kb = 0; kb < K / 64; ++kb) {
+            const uint64_t ad = tc_smem_desc(smem_u32(sA + kb * 128 * 128));
+            const uint64_t bd = tc_smem_desc(smem_u32(sB + kb * N * 128));
+#pragma unroll
+            for (int s = 0; s < 4; ++s) tc_mma(tb, ad + 2 * s, bd + 2 * s, idesc, (kb | s) != 0);
+        }
+        tc_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    for (int c = 0; c < N; c += 8) {
+        float v[8];
+        tmem_ld8(tb + ((uint32_t)(warp * 32) << 16) + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) D[tid * N + c + e] = v[e];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tb, 64);
+}
+
+extern "C" int toued_tc_gemm_test(const float* A, const float* B, void* scratch_img, float* D, void* stream) {
+    constexpr int N = 48, K = 256;
+    cudaStream_t st = (cudaStream_t)stream;
+    pack_b_sw128_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(B, (__half*)scratch_img, N, K);
+    TOUED_LAUNCH_CHECK();
+    const size_t smem = (K / 64) * 128 * 128 + (K / 64) * N * 128 + 1024;
+    TOUED_CUDA(cudaFuncSetAttribute(tc_gemm_test_kernel<N, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_gemm_test_kernel<N, K><<<1, 128, smem, st>>>(A, (const __half*)scratch_img, D);
+    TOUED_LAUNCH_CHECK();
+    return 0;
+}

@@ -60,6 +60,9 @@ class MetaGradWorkspace:
         self.whT = torch.empty((768, 256), dtype=f32, device=device)
         self.partials = torch.empty(_lib.lib().toued_lpg_wgrad_workspace_floats(), dtype=f32, device=device)
         self.loss_scal = torch.empty((N, 2), dtype=f32, device=device)
+        if self.tape.precision == "tc":                     # fp32 staging for the (still SIMT) reverse pass
+            self.h32 = torch.empty((L, R, 256), dtype=f32, device=device)
+            self.g32 = torch.empty((4, L, R, 256), dtype=f32, device=device)
         self.key = (N, W, L, obs_dim, K, n_params, str(device))
 
 
@@ -67,7 +70,8 @@ _WS_CACHE = {}
 
 
 def _workspace(n, w, L, D, K, P, device) -> MetaGradWorkspace:
-    key = (n, w, L, D, K, P, str(device))
+    import to_ued_b200
+    key = (n, w, L, D, K, P, str(device), to_ued_b200.GRU_PRECISION)
     ws = _WS_CACHE.get(key)
     if ws is None:
         _WS_CACHE.clear()
@@ -161,11 +165,16 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                       p(ws.d_pi_hat), p(ws.d_y_hat), nb, W, L, D, float(actor.learning_rate),
                       float(critic.learning_rate), float(actor.max_grad_norm),
                       float(lpg_hypers.agent_target_coeff), *[float(b) for b in bK], float(gscale), s)
-            _lib.call("toued_gru_backward", p(tape.done[k]), p(lpg), p(ws.whT), p(tape.h[k]), p(tape.gates[k]),
+            if tape.precision == "tc":
+                ws.h32.copy_(tape.h16[k]); ws.g32.copy_(tape.g16[k])
+                h_k, g_k = ws.h32, ws.g32
+            else:
+                h_k, g_k = tape.h[k], tape.gates[k]
+            _lib.call("toued_gru_backward", p(tape.done[k]), p(lpg), p(ws.whT), p(h_k), p(g_k),
                       p(tape.y_hat[k]), p(ws.d_pi_hat), p(ws.d_y_hat), p(ws.dl), p(ws.dx), nb, W, L, cond, s)
             first = (mb == 0 and k == K - 1)
             _lib.call("toued_lpg_wgrad", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg), p(tape.x[k]),
-                      p(tape.h[k]), p(tape.gates[k]), p(ws.d_pi_hat), p(ws.dl), p(ws.dx), p(ws.partials),
+                      p(h_k), p(g_k), p(ws.d_pi_hat), p(ws.dl), p(ws.dx), p(ws.partials),
                       nb, W, L, D, cond, 0 if first else 1, s)
         # ---- metrics (sums over agents; divided by n_global after the all-reduce) ----
         lpg_loss, value_loss = ws.loss_scal[:, 0], ws.loss_scal[:, 1]
