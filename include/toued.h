@@ -156,16 +156,23 @@ int toued_masked_reset(const void* levels, const uint8_t* mask, int32_t* state, 
 /* Unit check of the tcgen05 building blocks: D f32[128][48] = A f32[128][256] * B f32[48][256]^T with
  * fp16 operands / fp32 accumulation in TMEM.  scratch_img: 24 KiB device scratch.                  */
 int toued_tc_gemm_test(const float* A, const float* B, void* scratch_img, float* D, void* stream);
+/* Same for MN-major bf16 operands from token tile images: D f32[128][128] = A f32[128 k][128]^T * B f32[128 k][128]
+ * (the weight-gradient GEMM shape).  scratch_img: 64 KiB.                                           */
+int toued_tc_gemm_mn_test(const float* A, const float* B, void* scratch_img, float* D, int lbo, int sbo,
+                          int kadv, void* stream);
 
 /* Pack the recurrent matrix Wh into the fp16 SW128 pass images the tensor-core forward streams
  * (wh_img: 384 KiB, once per meta-step).                                                           */
 int toued_pack_wh_forward(const float* lpg_params, void* wh_img, void* stream);
 /* Tensor-core version of toued_gru_forward (models/lpg.py:11-30,77-84): fp16 operands, fp32
- * accumulation in TMEM.  h16 f16[L][R][256] and g16 f16[4][L][R][256] (r, z, n, Whn h + bhn) are
- * saved in half precision for the reverse pass; pi_hat / y_hat stay fp32.                          */
+ * accumulation in TMEM.  Saved for the reverse pass (NULL to skip):
+ *   h16   f16[L][R][256]      h_t
+ *   fac   f16[5][L][R][256]   factors f_r, f_z, f_hn, f_an (d pre-activation = dh * f) and z
+ *   hpimg bf16 token-tile image [L*Rp/64][4][64][64] of the masked carry h' used at each step
+ * pi_hat / y_hat stay fp32.                                                                        */
 int toued_gru_forward_tc(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,
-                         void* h16, void* g16, float* pi_hat, float* y_hat, int n_agents, int n_workers,
-                         int rollout_len, int lifetime_conditioning, void* stream);
+                         void* h16, void* fac, void* hpimg, float* pi_hat, float* y_hat, int n_agents,
+                         int n_workers, int rollout_len, int lifetime_conditioning, void* stream);
 
 #ifdef __cplusplus
 }

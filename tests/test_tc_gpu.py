@@ -22,6 +22,24 @@ def test_tcgen05_gemm_tile(built_lib):
     assert err < 2e-4, f"tcgen05 tile mismatch: max abs err {err}"
 
 
+def test_tcgen05_mn_major_gemm_tile(built_lib):
+    from to_ued_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(1)
+    A = torch.randn(128, 128, generator=g)          # [k][m]
+    B = torch.randn(128, 128, generator=g)          # [k][n]
+    img = torch.zeros(65536, dtype=torch.uint8, device="cuda")
+    D = torch.zeros(128, 128, device="cuda")
+    Ad, Bd = A.cuda(), B.cuda()                      # keep alive across the asynchronous launch
+    # MN-major SW128 descriptor: LBO = 8192 B between 64-element MN groups, SBO = 1024 B between 8-row
+    # k groups, +2048 B per K=16 step
+    _lib.call("toued_tc_gemm_mn_test", _lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(img), _lib.ptr(D), 8192, 1024, 2048,
+              _lib.stream_ptr())
+    torch.cuda.synchronize()
+    want = A.bfloat16().double().T @ B.bfloat16().double()
+    err = (D.cpu().double() - want).abs().max().item()
+    assert err < 2e-4, f"MN-major tcgen05 tile mismatch: max abs err {err}"
+
+
 @pytest.mark.parametrize("cond", [False, True])
 def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond):
     """Tensor-core GRU forward vs the exact-fp32 SIMT kernel on identical inputs.  Stated tolerance:
@@ -39,6 +57,8 @@ def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond):
     lpg = torch.from_numpy(c.lpg).cuda()
     p, s = _lib.ptr, _lib.stream_ptr()
     out = {}
+    global tape_tc_hpimg
+    tape_tc_hpimg = lambda o: o["hpimg"]
     traj, _, _, _ = ro.batch_rollout(c.keys, ag.actor_state, ag.level.packed, ag.env_obs, ag.env_state)
     for prec in ("fp32", "tc"):
         tape = Tape(n, c.w, c.L, c.D, K, "cuda", precision=prec)
@@ -50,15 +70,39 @@ def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond):
         if prec == "tc":
             _lib.call("toued_pack_wh_forward", p(lpg), p(tape.wh_img), s)
             _lib.call("toued_gru_forward_tc", p(tape.x[0]), p(tape.done[0]), p(lpg), p(tape.wh_img), p(tape.h16[0]),
-                      p(tape.g16[0]), p(tape.pi_hat[0]), p(tape.y_hat[0]), n, c.w, c.L, int(cond), s)
-            out[prec] = (tape.pi_hat[0].clone(), tape.y_hat[0].clone(), tape.h16[0].float(), tape.g16[0].float())
+                      p(tape.fac[0]), p(tape.hpimg[0]), p(tape.pi_hat[0]), p(tape.y_hat[0]), n, c.w, c.L, int(cond), s)
+            out[prec] = (tape.pi_hat[0].clone(), tape.y_hat[0].clone(), tape.h16[0].float(), tape.fac[0].float())
+            out["hpimg"] = tape.hpimg[0].clone()
         else:
             _lib.call("toued_gru_forward", p(tape.x[0]), p(tape.done[0]), p(lpg), p(tape.h[0]), p(tape.gates[0]),
                       p(tape.pi_hat[0]), p(tape.y_hat[0]), n, c.w, c.L, int(cond), s)
-            out[prec] = (tape.pi_hat[0].clone(), tape.y_hat[0].clone(), tape.h[0].clone(), tape.gates[0].clone())
+            r_, z_, n_, hn_ = tape.gates[0]
+            h_ = tape.h[0]
+            nd = (1 - tape.done[0].float()).permute(1, 0, 2).reshape(c.L, n * c.w, 1)     # [L][R][1]
+            hp_ = torch.cat([h_[1:], torch.zeros_like(h_[:1])], 0) * nd                  # masked carry
+            fan = (1 - z_) * (1 - n_ * n_)
+            fac_ref = torch.stack([fan * hn_ * r_ * (1 - r_), (hp_ - n_) * z_ * (1 - z_), fan * r_, fan, z_])
+            out[prec] = (tape.pi_hat[0].clone(), tape.y_hat[0].clone(), h_.clone(), fac_ref)
+            out["hp_ref"] = hp_
     torch.cuda.synchronize()
-    names = ("pi_hat", "y_hat", "h", "gates")
+    # masked carry image vs reference
+    from_img = _unpack_tile_img(tape_tc_hpimg(out), c.L * n * c.w, 256)
+    e = rel_err(from_img.float().cpu().numpy(), out["hp_ref"].reshape(-1, 256).cpu().numpy())
+    print(f"hp image: rel err {e:.2e}")
+    assert e < 5e-3
+    names = ("pi_hat", "y_hat", "h", "factors")
     for nm, a, b in zip(names, out["tc"], out["fp32"]):
         e = rel_err(a.cpu().numpy(), b.cpu().numpy())
         print(f"tc vs fp32 {nm}: rel err {e:.2e}")
         assert e < 3e-3, f"{nm}: {e}"
+
+
+def _unpack_tile_img(img_u8, n_tok, C):
+    """token tile image (uint8 tensor) -> bf16 [n_tok][C] (inverse of tile_img_offset in csrc/tc.cuh)."""
+    tok = torch.arange(n_tok, device=img_u8.device)
+    col = torch.arange(C, device=img_u8.device)
+    tb, r = tok // 64, tok % 64
+    cg, cin = col // 64, col % 64
+    off = ((tb[:, None] * (C // 64) + cg[None, :]) << 13) + r[:, None] * 128 + (((cin[None, :] >> 3) ^ (r[:, None] & 7)) << 4) + ((cin[None, :] & 7) << 1)
+    flat = img_u8.view(torch.bfloat16)
+    return flat[(off // 2).reshape(-1)].reshape(n_tok, C)

@@ -56,8 +56,10 @@ class Tape:
         if self.precision == "tc":
             f16 = torch.float16
             kk = K if keep_gates else 1                      # without a reverse pass one slot is enough
+            Rp = (R + 63) // 64 * 64
             self.h16 = torch.empty((kk, L, R, 256), dtype=f16, device=dev)
-            self.g16 = torch.empty((kk, 4, L, R, 256), dtype=f16, device=dev)
+            self.fac = torch.empty((kk, 5, L, R, 256), dtype=f16, device=dev) if keep_gates else None
+            self.hpimg = torch.empty((kk, L * Rp * 256 * 2), dtype=torch.uint8, device=dev) if keep_gates else None
             self.wh_img = torch.empty(256 * 768, dtype=f16, device=dev)
             self.wh_img_version = None
             self.h = self.gates = None
@@ -89,7 +91,8 @@ def lpg_agent_train_step(k, tape: Tape, levels, step, lpg_params, lifetime_condi
     if tape.precision == "tc":
         ks = k % tape.h16.shape[0]
         _lib.call("toued_gru_forward_tc", p(tape.x[k]), p(tape.done[k]), p(lpg_params), p(tape.wh_img),
-                  p(tape.h16[ks]), p(tape.g16[ks]), p(tape.pi_hat[k]), p(tape.y_hat[k]),
+                  p(tape.h16[ks]), p(tape.fac[ks]) if tape.fac is not None else None,
+                  p(tape.hpimg[ks]) if tape.hpimg is not None else None, p(tape.pi_hat[k]), p(tape.y_hat[k]),
                   N, W, L, int(lifetime_conditioning), s)
     else:
         _lib.call("toued_gru_forward", p(tape.x[k]), p(tape.done[k]), p(lpg_params), p(tape.h[k]),

@@ -10,7 +10,7 @@
 //     accumulator and commits to mbarriers;
 //   * 8 epilogue warps tcgen05.ld the three gate pre-activations of their (row, 8 units), add the fp32
 //     input projection x W_i + b_i, apply the flax GRUCell gate math, write h_t (fp16) into A[nxt] and
-//     h / r / z / n / (W_hn h + b_hn) (fp16) to HBM for the reverse pass, and accumulate the two heads
+//     h (fp16), the five reverse-pass factors (fp16) and the masked carry h' (bf16 tile image) to HBM, and accumulate the two heads
 //     (pi_hat, y_hat logits) on relu(h_t) in registers.
 // fp16 operands / fp32 accumulate: the hidden state is quantised to fp16 once per step (|h| < 1).
 // Parity is checked against the exact-fp32 SIMT kernel and the fp64 oracle with a stated tolerance.
@@ -49,8 +49,8 @@ template <int X>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ done,
                       const float* __restrict__ lpg, const __half* __restrict__ wh_img,
-                      __half* __restrict__ h16, __half* __restrict__ g16, float* __restrict__ pi_hat,
-                      float* __restrict__ y_hat, int R, int L, int W) {
+                      __half* __restrict__ h16, __half* __restrict__ fac, unsigned char* __restrict__ hpimg,
+                      float* __restrict__ pi_hat, float* __restrict__ y_hat, int R, int L, int W) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sA = smem;                                   // 2 x 64 KB
@@ -140,6 +140,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
         const int rsafe = rv ? row : 0;
         const int n_ag = rsafe / W, w_ag = rsafe % W;
         const size_t gs = (size_t)L * R * LPG_H;
+        const size_t Rp = ((size_t)R + 63) & ~(size_t)63;     // rows padded to the 64-token image blocks
         uint32_t it = 0;
         int cur = 0;
         for (int t = L - 1; t >= 0; --t) {
@@ -179,7 +180,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                 float hp[8];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hp2[e]); hp[2 * e] = f.x; hp[2 * e + 1] = f.y; }
-                float hv[8], rr[8], zz[8], nn[8], hn[8];
+                float hv[8], fr[8], fz[8], fhn[8], fan[8], zz[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int u = u0 + e;
@@ -190,11 +191,16 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                         gz = fmaf(xr[i], sWi[i * LPG_G + LPG_H + u], gz);
                         gn = fmaf(xr[i], sWi[i * LPG_G + 2 * LPG_H + u], gn);
                     }
-                    rr[e] = sigmoidf_(gr + ar[e]);
+                    const float rr = sigmoidf_(gr + ar[e]);
                     zz[e] = sigmoidf_(gz + az[e]);
-                    hn[e] = an[e] + sbhn[u];
-                    nn[e] = tanhf_(gn + rr[e] * hn[e]);
-                    hv[e] = (1.0f - zz[e]) * nn[e] + zz[e] * hp[e];
+                    const float hn = an[e] + sbhn[u];
+                    const float nn = tanhf_(gn + rr * hn);
+                    hv[e] = (1.0f - zz[e]) * nn + zz[e] * hp[e];
+                    // reverse-pass factors: d(pre-activation) = dh * factor   (lpg.py GRUCell backward)
+                    fan[e] = (1.0f - zz[e]) * (1.0f - nn * nn);          // dan = dh * fan
+                    fhn[e] = fan[e] * rr;                                 // d(Whn h + bhn) = dan * r
+                    fr[e] = fan[e] * hn * rr * (1.0f - rr);               // dar
+                    fz[e] = (hp[e] - nn) * zz[e] * (1.0f - zz[e]);        // daz
                     const float y = fmaxf(hv[e], 0.0f);
                     head[0] = fmaf(y, swp[u], head[0]);
 #pragma unroll
@@ -208,14 +214,33 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                     r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
                     return r;
                 };
+                auto pack8b = [](const float (&v)[8]) {
+                    uint4 r;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+                    r.x = *reinterpret_cast<uint32_t*>(&h0); r.y = *reinterpret_cast<uint32_t*>(&h1);
+                    r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
+                    return r;
+                };
                 const uint4 hpk = pack8(hv);
                 *reinterpret_cast<uint4*>(Anxt + soff) = zero_next ? make_uint4(0u, 0u, 0u, 0u) : hpk;
                 if (rv) {
                     *reinterpret_cast<uint4*>(h16 + tokbase + u0) = hpk;
-                    *reinterpret_cast<uint4*>(g16 + tokbase + u0) = pack8(rr);
-                    *reinterpret_cast<uint4*>(g16 + gs + tokbase + u0) = pack8(zz);
-                    *reinterpret_cast<uint4*>(g16 + 2 * gs + tokbase + u0) = pack8(nn);
-                    *reinterpret_cast<uint4*>(g16 + 3 * gs + tokbase + u0) = pack8(hn);
+                    if (fac) {
+                        *reinterpret_cast<uint4*>(fac + tokbase + u0) = pack8(fr);
+                        *reinterpret_cast<uint4*>(fac + gs + tokbase + u0) = pack8(fz);
+                        *reinterpret_cast<uint4*>(fac + 2 * gs + tokbase + u0) = pack8(fhn);
+                        *reinterpret_cast<uint4*>(fac + 3 * gs + tokbase + u0) = pack8(fan);
+                        *reinterpret_cast<uint4*>(fac + 4 * gs + tokbase + u0) = pack8(zz);
+                    }
+                    if (hpimg) {
+                        // h' consumed at step t-1 (= masked h_t), bf16 token-tile image for the weight-gradient GEMM
+                        if (t > 0)
+                            *reinterpret_cast<uint4*>(hpimg + tile_img_offset((size_t)(t - 1) * Rp + row, 4, u0)) =
+                                zero_next ? make_uint4(0u, 0u, 0u, 0u) : pack8b(hv);
+                        if (t == L - 1)
+                            *reinterpret_cast<uint4*>(hpimg + tile_img_offset((size_t)t * Rp + row, 4, u0)) = make_uint4(0u, 0u, 0u, 0u);
+                    }
                 }
             }
             // A[nxt] complete for this thread: make it visible to the async proxy, signal the MMA warp
@@ -254,8 +279,8 @@ static size_t gru_fwd_tc_smem(int X) {
 }
 
 extern "C" int toued_gru_forward_tc(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,
-                                    void* h16, void* g16, float* pi_hat, float* y_hat, int n_agents, int n_workers,
-                                    int rollout_len, int lifetime_conditioning, void* stream) {
+                                    void* h16, void* fac, void* hpimg, float* pi_hat, float* y_hat, int n_agents,
+                                    int n_workers, int rollout_len, int lifetime_conditioning, void* stream) {
     const int R = n_agents * n_workers;
     TOUED_CHECK(R > 0 && rollout_len > 0, "toued_gru_forward_tc: empty problem");
     const int blocks = (R + FT_M - 1) / FT_M;
@@ -264,12 +289,12 @@ extern "C" int toued_gru_forward_tc(const float* x, const uint8_t* done, const f
         const size_t smem = gru_fwd_tc_smem(7);
         TOUED_CUDA(cudaFuncSetAttribute(gru_forward_tc_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gru_forward_tc_kernel<7><<<blocks, FT_THREADS, smem, st>>>(x, done, lpg_params, (const __half*)wh_img, (__half*)h16,
-                                                                    (__half*)g16, pi_hat, y_hat, R, rollout_len, n_workers);
+                                                                    (__half*)fac, (unsigned char*)hpimg, pi_hat, y_hat, R, rollout_len, n_workers);
     } else {
         const size_t smem = gru_fwd_tc_smem(5);
         TOUED_CUDA(cudaFuncSetAttribute(gru_forward_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gru_forward_tc_kernel<5><<<blocks, FT_THREADS, smem, st>>>(x, done, lpg_params, (const __half*)wh_img, (__half*)h16,
-                                                                    (__half*)g16, pi_hat, y_hat, R, rollout_len, n_workers);
+                                                                    (__half*)fac, (unsigned char*)hpimg, pi_hat, y_hat, R, rollout_len, n_workers);
     }
     TOUED_LAUNCH_CHECK();
     return 0;

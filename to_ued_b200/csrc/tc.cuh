@@ -22,8 +22,29 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(int rows, int row, int
            (uint32_t)((kin & 7) << 1);
 }
 
+// "Token tile image": a [tokens][C] 16-bit matrix stored as 64-token x 64-column sub-tiles of 8 KB,
+// each already in the SW128 pattern (row = token, 128 B per row, chunk ^= row & 7), sub-tiles ordered
+// [token block][column group].  A sub-tile is at once (a) a K-major SW128 K-block with K = columns and
+// (b) an MN-major SW128 atom column with K = tokens, so it can be bulk-copied into shared memory and
+// fed to tcgen05.mma for both the recurrence GEMMs and the weight-gradient GEMMs.
+__host__ __device__ __forceinline__ size_t tile_img_offset(size_t tok, int n_col_groups, int col) {
+    const size_t tb = tok >> 6; const int r = (int)(tok & 63), cg = col >> 6, cin = col & 63;
+    return ((tb * n_col_groups + cg) << 13) + (size_t)r * 128 + (size_t)(((cin >> 3) ^ (r & 7)) << 4) + (size_t)((cin & 7) << 1);
+}
+
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// MN-major SW128 operand (contraction index = rows of the tile image): 64 MN-elements (128 B) per k-row,
+// 8 k-rows per 1024-byte swizzle atom (SBO), next group of 64 MN-elements `lbo_bytes` away (LBO).
+__device__ __forceinline__ uint64_t tc_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | (64ull << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor with both operands MN-major (weight-gradient GEMMs)
+__host__ __device__ constexpr uint32_t tc_idesc_mn(int M, int N, int fmt) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | (1u << 15) | (1u << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // instruction descriptor, kind::f16, fp32 accumulate, both operands K-major. fmt: 0 = f16, 1 = bf16
 __host__ __device__ constexpr uint32_t tc_idesc(int M, int N, int fmt) {

@@ -80,3 +80,76 @@ extern "C" int toued_tc_gemm_test(const float* A, const float* B, void* scratch_
     TOUED_LAUNCH_CHECK();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// MN-major check: D[128][128] = sum_k A[k][m] * B[k][n], K = 128 "tokens", bf16 token tile images.
+__global__ void pack_tile_img_kernel(const float* __restrict__ X, __nv_bfloat16* __restrict__ img, int K, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * C) return;
+    const int k = i / C, c = i % C;
+    *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(img) + tile_img_offset(k, C / 64, c)) = __float2bfloat16_rn(X[i]);
+}
+
+__global__ void __launch_bounds__(128, 1)
+tc_gemm_mn_test_kernel(const unsigned char* __restrict__ Aimg, const unsigned char* __restrict__ Bimg, float* __restrict__ D,
+                       uint32_t lbo, uint32_t sbo, uint32_t kadv) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sA = smem;               // 2 token blocks x [2 col groups][8 KB]
+    unsigned char* sB = smem + 32768;
+    __shared__ __align__(8) uint64_t bar_ld, bar_mma;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc(&tmem_base, 128);
+    if (tid == 0) { mbar_init(&bar_ld, 1); mbar_init(&bar_mma, 1); mbar_fence_init(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tmem_base;
+    if (tid == 0) {
+        mbar_expect_tx(&bar_ld, 65536);
+        bulk_g2s(sA, Aimg, 32768, &bar_ld);
+        bulk_g2s(sB, Bimg, 32768, &bar_ld);
+        mbar_wait(&bar_ld, 0);
+        tc_fence_after();
+        constexpr uint32_t idesc = tc_idesc_mn(128, 128, 1);
+        for (int blk = 0; blk < 2; ++blk)
+            for (int ks = 0; ks < 4; ++ks) {
+                auto mk = [&](uint32_t addr) {
+                    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+                           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+                };
+                const uint64_t ad = mk(smem_u32(sA + blk * 16384 + ks * kadv));
+                const uint64_t bd = mk(smem_u32(sB + blk * 16384 + ks * kadv));
+                tc_mma(tb, ad, bd, idesc, (blk | ks) != 0);
+            }
+        tc_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    for (int c = 0; c < 128; c += 8) {
+        float v[8];
+        tmem_ld8(tb + ((uint32_t)(warp * 32) << 16) + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) D[tid * 128 + c + e] = v[e];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tb, 128);
+}
+
+extern "C" int toued_tc_gemm_mn_test(const float* A, const float* B, void* scratch_img, float* D, int lbo, int sbo,
+                                     int kadv, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* ia = (unsigned char*)scratch_img;
+    unsigned char* ib = ia + 32768;
+    pack_tile_img_kernel<<<(128 * 128 + 255) / 256, 256, 0, st>>>(A, (__nv_bfloat16*)ia, 128, 128);
+    pack_tile_img_kernel<<<(128 * 128 + 255) / 256, 256, 0, st>>>(B, (__nv_bfloat16*)ib, 128, 128);
+    TOUED_LAUNCH_CHECK();
+    const size_t smem = 65536 + 1024;
+    TOUED_CUDA(cudaFuncSetAttribute(tc_gemm_mn_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_gemm_mn_test_kernel<<<1, 128, smem, st>>>(ia, ib, D, (uint32_t)lbo, (uint32_t)sbo, (uint32_t)kadv);
+    TOUED_LAUNCH_CHECK();
+    return 0;
+}
