@@ -135,7 +135,13 @@ int toued_lpg_wgrad(const int32_t* obs, const uint8_t* done, const float* critic
                     const float* d_pi_hat, const float* dl, const float* dx, float* workspace,
                     int n_agents, int n_workers, int rollout_len, int obs_dim,
                     int lifetime_conditioning, int accumulate, void* stream);
-int toued_reduce_partials(const float* workspace, float* grad, int lifetime_conditioning, void* stream);
+int toued_lpg_wgrad_workspace_offset(int which);   /* float offset of the {0: Wh, 1: small, 2: embed} partial area */
+int toued_lpg_wgrad_embed(const int32_t* obs, const uint8_t* done, const float* critic, const float* lpg_params,
+                          const float* dx, float* workspace, int n_agents, int n_workers, int rollout_len,
+                          int obs_dim, int lifetime_conditioning, int accumulate, void* stream);
+/* wh_splits: number of Wh partial slices to sum (32 after toued_lpg_wgrad, toued_wgrad_tc_splits() after
+ * toued_lpg_wgrad_tc).                                                                              */
+int toued_reduce_partials(const float* workspace, float* grad, int lifetime_conditioning, int wh_splits, void* stream);
 
 /* models/optim.py:12-17: optax.scale_by_adam -> scale(lr) -> scale(-1); count is 1-based.          */
 int toued_adam(float* params, const float* grad, float* mu, float* nu, int n, int count, float lr,
@@ -173,6 +179,22 @@ int toued_pack_wh_forward(const float* lpg_params, void* wh_img, void* stream);
 int toued_gru_forward_tc(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,
                          void* h16, void* fac, void* hpimg, float* pi_hat, float* y_hat, int n_agents,
                          int n_workers, int rollout_len, int lifetime_conditioning, void* stream);
+
+/* Pack Wh into the bf16 SW128 chunk images of the tensor-core reverse pass (384 KiB).               */
+int toued_pack_wh_backward(const float* lpg_params, void* whb_img, void* stream);
+/* Tensor-core BPTT (reverse of toued_gru_forward_tc).  Reads h16 / fac saved by the forward; writes
+ *   dgimg bf16 token-tile image [L*Rp/64][16][64][64]: column groups 0-3 dar, 4-7 daz, 8-11 dhn, 12-15 dan
+ *   dl f32[L][R][8] head-logit cotangents, dx f32[L][R][2] (d pyt, d pyt1)                          */
+int toued_gru_backward_tc(const uint8_t* done, const float* lpg_params, const void* whb_img,
+                          const void* h16, const void* fac, const float* y_hat, const float* d_pi_hat,
+                          const float* d_y_hat, void* dgimg, float* dl, float* dx, int n_agents,
+                          int n_workers, int rollout_len, int lifetime_conditioning, void* stream);
+/* Tensor-core weight gradients from the token tile images (hpimg from the forward, dgimg from the
+ * backward) + streaming small gradients; partial areas of the toued_lpg_wgrad workspace.             */
+int toued_wgrad_tc_splits(void);
+int toued_lpg_wgrad_tc(const void* hpimg, const void* dgimg, const float* x, const void* h16,
+                       const float* d_pi_hat, const float* dl, float* wh_partials, float* small_partials,
+                       int n_agents, int n_workers, int rollout_len, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

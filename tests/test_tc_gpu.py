@@ -106,3 +106,42 @@ def _unpack_tile_img(img_u8, n_tok, C):
     off = ((tb[:, None] * (C // 64) + cg[None, :]) << 13) + r[:, None] * 128 + (((cin[None, :] >> 3) ^ (r[:, None] & 7)) << 4) + ((cin[None, :] & 7) << 1)
     flat = img_u8.view(torch.bfloat16)
     return flat[(off // 2).reshape(-1)].reshape(n_tok, C)
+
+
+@pytest.mark.parametrize("mode,cond", [("all_shortlife", False), ("all_vrandlife", True)])
+def test_meta_gradient_tensor_core_path(built_lib, mode, cond, monkeypatch):
+    """Full LPG meta-gradient with the tensor-core GRU (fp16 forward, bf16 reverse operands, fp32
+    accumulation in TMEM) against the fp64 autograd oracle on the same trajectories.
+    Stated tolerance: every parameter block within 2e-2 of the oracle relative to the block's max |g|,
+    and the whole gradient within 1e-2 in relative L2 norm."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    import to_ued_b200
+    monkeypatch.setattr(to_ued_b200, "GRU_PRECISION", "tc")
+    import numpy as np
+    from helpers import Case, to_oracle_traj, rel_err
+    from oracle import prng
+    from oracle.agents import AgentTables
+    from oracle.meta import lpg_meta_grad_train_step as o_step
+    from test_meta_grad_gpu import _run
+    K, n = 5, 4
+    c = Case(mode, n=n, seed=7, cond=cond, table_scale=0.3, lifetimes=[250, 3, 250, 250], steps=[0, 0, 17, 246])
+    (new_ts, ag2, vc2, met), ws = _run(c, K)
+    assert ws.tape.precision == "tc"
+    tape = ws.tape
+    trajs = [to_oracle_traj(tape.transition(k)) for k in range(K)]
+    ev = to_oracle_traj(tape.transition(K))
+    dt = torch.float64
+    oag = AgentTables(torch.tensor(c.actor).to(dt), torch.tensor(c.critic).to(dt), torch.tensor(c.steps.astype(np.int64)))
+    s0 = c.oro.batch_reset(None, c.p, c.w)
+    o = o_step(prng.PRNGKey(21), c.layout, torch.tensor(c.lpg).to(dt), oag, torch.tensor(c.value).to(dt), c.oro, c.p,
+               s0, c.life, num_agent_updates=K, trajectories=trajs, eval_trajectory=ev, do_eval=False)
+    g = met["_grad"].cpu().numpy().astype(np.float64)
+    og = o["grad"].numpy()
+    for name, (off, cnt, shp) in c.layout.offsets.items():
+        e = rel_err(g[off:off + cnt], og[off:off + cnt])
+        print(f"  block {name:5s} rel err {e:.2e}")
+        assert e < 2e-2, f"meta-gradient block {name}: rel err {e:.3e}"
+    l2 = np.linalg.norm(g - og) / np.linalg.norm(og)
+    print(f"[tc {mode}] relative L2 error of the meta-gradient {l2:.2e}")
+    assert l2 < 1e-2

@@ -47,7 +47,13 @@ SIGNATURES = {
     "toued_gru_backward": [_P] * 10 + [_I] * 4 + [_P],
     "toued_lpg_wgrad_workspace_floats": [],
     "toued_lpg_wgrad": [_P] * 11 + [_I] * 6 + [_P],
-    "toued_reduce_partials": [_P, _P, _I, _P],
+    "toued_reduce_partials": [_P, _P, _I, _I, _P],
+    "toued_lpg_wgrad_workspace_offset": [_I],
+    "toued_lpg_wgrad_embed": [_P] * 6 + [_I] * 6 + [_P],
+    "toued_pack_wh_backward": [_P] * 3,
+    "toued_gru_backward_tc": [_P] * 11 + [_I] * 4 + [_P],
+    "toued_wgrad_tc_splits": [],
+    "toued_lpg_wgrad_tc": [_P] * 8 + [_I] * 4 + [_P],
     "toued_adam": [_P] * 4 + [_I, _I] + [_F] * 4 + [_P],
     "toued_init_tables": [_P] * 3 + [_I] * 3 + [_P],
     "toued_masked_reset": [_P] * 5 + [_I] * 3 + [_P],
@@ -86,7 +92,7 @@ def stream_ptr():
 
 
 # kernels launched by one call of each entry point (for the bench's gpu_launches count)
-KERNELS_PER_CALL = {"toued_lpg_wgrad": 3, "toued_init_tables": 2}
+KERNELS_PER_CALL = {"toued_lpg_wgrad": 3, "toued_init_tables": 2, "toued_lpg_wgrad_tc": 2}
 LAUNCHES = {}          # entry point -> number of calls since reset_counters()
 PROFILE = None         # when a dict: entry point -> list of (start, end) CUDA events
 

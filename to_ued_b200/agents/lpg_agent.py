@@ -59,7 +59,8 @@ class Tape:
             Rp = (R + 63) // 64 * 64
             self.h16 = torch.empty((kk, L, R, 256), dtype=f16, device=dev)
             self.fac = torch.empty((kk, 5, L, R, 256), dtype=f16, device=dev) if keep_gates else None
-            self.hpimg = torch.empty((kk, L * Rp * 256 * 2), dtype=torch.uint8, device=dev) if keep_gates else None
+            # bf16 token-tile image of the masked carry (rows >= R of a partial 64-token block stay zero)
+            self.hpimg = torch.zeros((kk, L * Rp * 256 * 2), dtype=torch.uint8, device=dev) if keep_gates else None
             self.wh_img = torch.empty(256 * 768, dtype=f16, device=dev)
             self.wh_img_version = None
             self.h = self.gates = None

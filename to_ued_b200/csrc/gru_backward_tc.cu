@@ -1,0 +1,281 @@
+// Tensor-core GRU backward (BPTT) for the LPG network — the reverse of gru_forward_tc.cu, i.e. the part
+// of jax.grad(_train_agent) (meta/train.py:121-128) that flows through models/lpg.py:11-30,77-84.
+//
+// A CTA owns 128 sequences and walks t = 0 .. L-1 (the forward scan is reversed).  Per step
+//     dh_t   = relu'(h_t) * (d pi_hat * w_pi + dl . W_y)  +  (1 - done_{t-1}) * carry
+//     dG_g   = dh_t * f_g            (f_r, f_z, f_hn, f_an saved by the forward epilogue)
+//     carry' = dGh @ Wh^T + z * dh_t
+// The carry stays in fp32 in TMEM (two 256-column sets, ping-pong): dGh @ Wh^T is accumulated by
+// tcgen05.mma from bf16 operands (dG written by the epilogue warps into SW128 smem chunks, Wh chunks
+// streamed by a TMA-producer warp), and the element-wise z*dh_t term is injected into the same
+// accumulator by a tiny identity MMA on a bf16 hi/lo pair, so the recurrent chain keeps ~16 mantissa
+// bits without ever leaving tensor memory.
+// Outputs for the weight-gradient kernels: dG (dar, daz, dhn, dan) as a bf16 token-tile image,
+// the head-logit cotangents dl and d pyt / d pyt1.
+#include "tc.cuh"
+#include "lpg_common.cuh"
+#include "../../include/toued.h"
+
+constexpr int BT_M = 128;
+constexpr int BT_THREADS = 320;
+constexpr int BT_ACHUNK = BT_M * 128;            // 16 KB: [128 rows][64 bf16]
+constexpr int BT_ASTAGE = 5 * BT_ACHUNK;         // dG_r, dG_z, dG_hn, cz_hi, cz_lo
+constexpr int BT_BCHUNK = LPG_H * 128;           // 32 KB: [256 units][64 c]
+constexpr int BT_NSB = 3;
+constexpr int BT_ICHUNK = 64 * 128;              // 8 KB identity
+
+// Wh[j][c] -> 12 bf16 K-major SW128 chunk images [cc = c / 64][row j][k = c % 64]
+__global__ void pack_wh_bwd_kernel(const float* __restrict__ Wh, __nv_bfloat16* __restrict__ img) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= LPG_H * LPG_G) return;
+    const int j = i / LPG_G, c = i % LPG_G;
+    char* base = reinterpret_cast<char*>(img) + (size_t)(c >> 6) * BT_BCHUNK;
+    *reinterpret_cast<__nv_bfloat16*>(base + sw128_offset(LPG_H, j, c & 63)) = __float2bfloat16_rn(Wh[i]);
+}
+
+extern "C" int toued_pack_wh_backward(const float* lpg_params, void* whb_img, void* stream) {
+    pack_wh_bwd_kernel<<<(LPG_H * LPG_G + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        lpg_params + lpg_offsets(5).Wh, (__nv_bfloat16*)whb_img);
+    TOUED_LAUNCH_CHECK();
+    return 0;
+}
+
+__device__ __forceinline__ void unpack8h(const uint4& r, float (&v)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+}
+__device__ __forceinline__ uint4 pack8bf(const float (&v)[8]) {
+    uint4 r;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+    r.x = *reinterpret_cast<uint32_t*>(&h0); r.y = *reinterpret_cast<uint32_t*>(&h1);
+    r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
+    return r;
+}
+
+__global__ void __launch_bounds__(BT_THREADS, 1)
+gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict__ lpg, int X,
+                       const unsigned char* __restrict__ whb_img, const __half* __restrict__ h16,
+                       const __half* __restrict__ fac, const float* __restrict__ y_hat,
+                       const float* __restrict__ d_pi_hat, const float* __restrict__ d_y_hat,
+                       unsigned char* __restrict__ dgimg, float* __restrict__ dl_out, float* __restrict__ dx,
+                       int R, int L, int W) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sA = smem;                                   // 80 KB
+    unsigned char* sB = sA + BT_ASTAGE;                         // 3 x 32 KB
+    unsigned char* sI = sB + BT_NSB * BT_BCHUNK;                // 8 KB identity
+    float* swp = reinterpret_cast<float*>(sI + BT_ICHUNK);      // [256]
+    float* sWy = swp + LPG_H;                                   // [256][8]
+    float* sWi = sWy + LPG_H * LPG_Y;                           // [2][768] rows 3, 4 of Wi
+    float* sdx = sWi + 2 * LPG_G;                               // [128][2]
+    __shared__ __align__(8) uint64_t b_full[BT_NSB], b_empty[BT_NSB], a_full, a_empty, q_full;
+    __shared__ uint32_t tmem_base_s;
+
+    const LpgOffsets o = lpg_offsets(X);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * BT_M;
+
+    if (tid == 0) {
+        for (int s = 0; s < BT_NSB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        mbar_init(&a_full, 8); mbar_init(&a_empty, 1); mbar_init(&q_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 9) tmem_alloc(&tmem_base_s, 512);
+    for (int i = tid; i < LPG_H; i += BT_THREADS) swp[i] = lpg[o.w_pi + i];
+    for (int i = tid; i < LPG_H * LPG_Y; i += BT_THREADS) sWy[i] = lpg[o.W_y + i];
+    for (int i = tid; i < 2 * LPG_G; i += BT_THREADS) sWi[i] = lpg[o.Wi + 3 * LPG_G + i];
+    for (int i = tid; i < 64 * 64; i += BT_THREADS) {
+        const int n = i >> 6, k = i & 63;
+        *reinterpret_cast<__nv_bfloat16*>(sI + sw128_offset(64, n, k)) = __float2bfloat16_rn(n == k ? 1.0f : 0.0f);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 8) {
+        // ===================== TMA producer: Wh chunks in (unit block, gate) order ====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = 0; t + 1 < L; ++t)
+                for (int ub = 0; ub < 4; ++ub)
+                    for (int g = 0; g < 3; ++g, ++it) {
+                        const int s = it % BT_NSB;
+                        mbar_wait(&b_empty[s], ((it / BT_NSB) & 1) ^ 1);
+                        mbar_expect_tx(&b_full[s], BT_BCHUNK);
+                        bulk_g2s(sB + s * BT_BCHUNK, whb_img + (size_t)(g * 4 + ub) * BT_BCHUNK, BT_BCHUNK, &b_full[s]);
+                    }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer =============================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc256 = tc_idesc(BT_M, 256, 1), idesc64 = tc_idesc(BT_M, 64, 1);
+            const uint32_t a_addr = smem_u32(sA), i_addr = smem_u32(sI);
+            uint32_t it = 0, ait = 0;
+            for (int t = 0; t + 1 < L; ++t) {
+                const uint32_t q_addr = tmem_base + (t & 1) * 256;
+                for (int ub = 0; ub < 4; ++ub, ++ait) {
+                    mbar_wait(&a_full, ait & 1);
+                    tc_fence_after();
+                    for (int g = 0; g < 3; ++g, ++it) {
+                        const int s = it % BT_NSB;
+                        mbar_wait(&b_full[s], (it / BT_NSB) & 1);
+                        tc_fence_after();
+                        const uint64_t ad = tc_smem_desc(a_addr + g * BT_ACHUNK);
+                        const uint64_t bd = tc_smem_desc(smem_u32(sB + s * BT_BCHUNK));
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) tc_mma(q_addr, ad + 2 * ks, bd + 2 * ks, idesc256, (ub | g | ks) != 0);
+                        tc_commit(&b_empty[s]);
+                    }
+                    // z * dh_t (bf16 hi + lo) through the identity: accumulates onto columns [64 ub, 64 ub + 64)
+                    const uint64_t idd = tc_smem_desc(i_addr);
+#pragma unroll
+                    for (int c = 3; c < 5; ++c) {
+                        const uint64_t ad = tc_smem_desc(a_addr + c * BT_ACHUNK);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) tc_mma(q_addr + ub * 64, ad + 2 * ks, idd + 2 * ks, idesc64, 1u);
+                    }
+                    tc_commit(&a_empty);
+                }
+                tc_commit(&q_full);
+            }
+        }
+    } else {
+        // ===================== epilogue / producer-of-A warps 0..7 =====================================
+        const int q = warp & 3, hf = warp >> 2;
+        const int rl = q * 32 + lane;
+        const int row = row0 + rl;
+        const bool rv = row < R;
+        const int rsafe = rv ? row : 0;
+        const int n_ag = rsafe / W, w_ag = rsafe % W;
+        const size_t gs = (size_t)L * R * LPG_H;
+        const size_t Rp = ((size_t)R + 63) & ~(size_t)63;
+        uint32_t ait = 0;
+        for (int t = 0; t < L; ++t) {
+            const size_t tok = (size_t)t * R + rsafe;
+            // head cotangents of this row (softmax backward of y_hat), lpg.py:83-84
+            float dl[8], dpi;
+            {
+                float yh[8], dy[8];
+                const float4* q0 = reinterpret_cast<const float4*>(y_hat + tok * 8);
+                const float4* q1 = reinterpret_cast<const float4*>(d_y_hat + tok * 8);
+                const float4 a0 = q0[0], a1 = q0[1], b0 = q1[0], b1 = q1[1];
+                yh[0] = a0.x; yh[1] = a0.y; yh[2] = a0.z; yh[3] = a0.w; yh[4] = a1.x; yh[5] = a1.y; yh[6] = a1.z; yh[7] = a1.w;
+                dy[0] = b0.x; dy[1] = b0.y; dy[2] = b0.z; dy[3] = b0.w; dy[4] = b1.x; dy[5] = b1.y; dy[6] = b1.z; dy[7] = b1.w;
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s = fmaf(yh[i], dy[i], s);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dl[i] = rv ? yh[i] * (dy[i] - s) : 0.0f;
+                dpi = rv ? d_pi_hat[tok] : 0.0f;
+                if (hf == 0 && rv) {
+                    float4* qo = reinterpret_cast<float4*>(dl_out + tok * 8);
+                    qo[0] = make_float4(dl[0], dl[1], dl[2], dl[3]);
+                    qo[1] = make_float4(dl[4], dl[5], dl[6], dl[7]);
+                }
+            }
+            // carry mask: the cell at step t-1 consumed (1 - done_{t-1}) * h_t
+            const float nd = (t > 0 && rv && !done[((size_t)n_ag * L + (t - 1)) * W + w_ag]) ? 1.0f : 0.0f;
+            if (t > 0) { mbar_wait(&q_full, (t - 1) & 1); tc_fence_after(); }
+            const uint32_t p_addr = tmem_base + ((t - 1) & 1) * 256 + ((uint32_t)(q * 32) << 16);
+            float dx3 = 0.f, dx4 = 0.f;
+            for (int ub = 0; ub < 4; ++ub) {
+                const int ubase = ub * 64 + hf * 32;                 // first of this thread's 32 units
+                uint4 outA[5][4];
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    const int u0 = ubase + c8 * 8;
+                    float carry[8];
+                    if (t > 0) {
+                        tmem_ld8(p_addr + u0, carry);
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) carry[e] = 0.f;
+                    }
+                    float fr[8], fz[8], fhn[8], fan[8], zz[8], hv[8];
+                    const size_t base = tok * LPG_H + u0;
+                    unpack8h(*reinterpret_cast<const uint4*>(fac + base), fr);
+                    unpack8h(*reinterpret_cast<const uint4*>(fac + gs + base), fz);
+                    unpack8h(*reinterpret_cast<const uint4*>(fac + 2 * gs + base), fhn);
+                    unpack8h(*reinterpret_cast<const uint4*>(fac + 3 * gs + base), fan);
+                    unpack8h(*reinterpret_cast<const uint4*>(fac + 4 * gs + base), zz);
+                    unpack8h(*reinterpret_cast<const uint4*>(h16 + base), hv);
+                    float gr[8], gz[8], ghn[8], gan[8], czh[8], czl[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int u = u0 + e;
+                        float dh = nd * carry[e];
+                        if (hv[e] > 0.0f) {
+                            float hd = dpi * swp[u];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) hd = fmaf(dl[i], sWy[u * 8 + i], hd);
+                            dh += hd;
+                        }
+                        if (!rv) dh = 0.0f;
+                        gr[e] = dh * fr[e]; gz[e] = dh * fz[e]; ghn[e] = dh * fhn[e]; gan[e] = dh * fan[e];
+                        const float cz = dh * zz[e];
+                        czh[e] = __bfloat162float(__float2bfloat16_rn(cz));
+                        czl[e] = cz - czh[e];
+                        dx3 = fmaf(gr[e], sWi[u], fmaf(gz[e], sWi[LPG_H + u], fmaf(gan[e], sWi[2 * LPG_H + u], dx3)));
+                        dx4 = fmaf(gr[e], sWi[LPG_G + u], fmaf(gz[e], sWi[LPG_G + LPG_H + u], fmaf(gan[e], sWi[LPG_G + 2 * LPG_H + u], dx4)));
+                    }
+                    outA[0][c8] = pack8bf(gr); outA[1][c8] = pack8bf(gz); outA[2][c8] = pack8bf(ghn);
+                    outA[3][c8] = pack8bf(czh); outA[4][c8] = pack8bf(czl);
+                    if (rv) {      // token tile image for the weight-gradient kernels: 16 column groups
+                        const size_t itok = (size_t)t * Rp + row;
+                        const int cin = hf * 32 + c8 * 8;
+                        *reinterpret_cast<uint4*>(dgimg + tile_img_offset(itok, 16, (0 * 4 + ub) * 64 + cin)) = outA[0][c8];
+                        *reinterpret_cast<uint4*>(dgimg + tile_img_offset(itok, 16, (1 * 4 + ub) * 64 + cin)) = outA[1][c8];
+                        *reinterpret_cast<uint4*>(dgimg + tile_img_offset(itok, 16, (2 * 4 + ub) * 64 + cin)) = outA[2][c8];
+                        *reinterpret_cast<uint4*>(dgimg + tile_img_offset(itok, 16, (3 * 4 + ub) * 64 + cin)) = pack8bf(gan);
+                    }
+                }
+                if (t + 1 < L) {
+                    // the MMAs of the previous unit block must have consumed the A stage
+                    mbar_wait(&a_empty, (ait & 1) ^ 1);
+#pragma unroll
+                    for (int c = 0; c < 5; ++c)
+#pragma unroll
+                        for (int c8 = 0; c8 < 4; ++c8)
+                            *reinterpret_cast<uint4*>(sA + c * BT_ACHUNK + sw128_offset(BT_M, rl, hf * 32 + c8 * 8)) = outA[c][c8];
+                    fence_proxy_async_smem();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_full);
+                    ++ait;
+                }
+            }
+            // d pyt / d pyt1: combine the two unit halves of the row
+            if (hf == 1) { sdx[rl * 2] = dx3; sdx[rl * 2 + 1] = dx4; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (hf == 0 && rv) *reinterpret_cast<float2*>(dx + ((size_t)t * R + row) * 2) = make_float2(dx3 + sdx[rl * 2], dx4 + sdx[rl * 2 + 1]);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
+static size_t gru_bwd_tc_smem() {
+    return BT_ASTAGE + BT_NSB * BT_BCHUNK + BT_ICHUNK + sizeof(float) * (LPG_H + LPG_H * LPG_Y + 2 * LPG_G + BT_M * 2) + 1024;
+}
+
+extern "C" int toued_gru_backward_tc(const uint8_t* done, const float* lpg_params, const void* whb_img,
+                                     const void* h16, const void* fac, const float* y_hat, const float* d_pi_hat,
+                                     const float* d_y_hat, void* dgimg, float* dl, float* dx, int n_agents,
+                                     int n_workers, int rollout_len, int lifetime_conditioning, void* stream) {
+    const int R = n_agents * n_workers;
+    TOUED_CHECK(R > 0 && rollout_len > 0, "toued_gru_backward_tc: empty problem");
+    const size_t smem = gru_bwd_tc_smem();
+    TOUED_CUDA(cudaFuncSetAttribute(gru_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gru_backward_tc_kernel<<<(R + BT_M - 1) / BT_M, BT_THREADS, smem, (cudaStream_t)stream>>>(
+        done, lpg_params, lifetime_conditioning ? 7 : 5, (const unsigned char*)whb_img, (const __half*)h16,
+        (const __half*)fac, y_hat, d_pi_hat, d_y_hat, (unsigned char*)dgimg, dl, dx, R, rollout_len, n_workers);
+    TOUED_LAUNCH_CHECK();
+    return 0;
+}

@@ -425,7 +425,8 @@ embed_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
     }
 }
 
-constexpr int WG_SPLITS = 32;        // token splits of the dWh SGEMM
+constexpr int WG_SPLITS = 37;        // token splits of the dWh GEMM (SIMT uses 32 of them, the tensor-core kernel 37)
+constexpr int WG_SPLITS_SIMT = 32;
 constexpr int SM_SPLITS = 592;       // 4 per SM for the streaming kernels
 constexpr int EM_SPLITS = 296;
 
@@ -447,8 +448,8 @@ extern "C" int toued_lpg_wgrad(const int32_t* obs, const uint8_t* done, const fl
     float* p_em = p_sm + (size_t)SM_SPLITS * SM_TOTAL;
     {
         const size_t chunks = (ntok + WG_KC - 1) / WG_KC;
-        const int cps = (int)((chunks + WG_SPLITS - 1) / WG_SPLITS);
-        wgrad_wh_kernel<<<dim3(LPG_G / 64, LPG_H / 64, WG_SPLITS), 256, 0, st>>>(done, h, dgates, p_wh, R, L, n_workers, cps, accumulate);
+        const int cps = (int)((chunks + WG_SPLITS_SIMT - 1) / WG_SPLITS_SIMT);
+        wgrad_wh_kernel<<<dim3(LPG_G / 64, LPG_H / 64, WG_SPLITS_SIMT), 256, 0, st>>>(done, h, dgates, p_wh, R, L, n_workers, cps, accumulate);
         TOUED_LAUNCH_CHECK();
     }
     {
@@ -463,15 +464,15 @@ extern "C" int toued_lpg_wgrad(const int32_t* obs, const uint8_t* done, const fl
 }
 
 // grad = sum over splits of the three partial groups, scattered to the flat parameter layout
-__global__ void reduce_partials_kernel(const float* __restrict__ ws, float* __restrict__ grad, int X) {
+__global__ void reduce_partials_kernel(const float* __restrict__ ws, float* __restrict__ grad, int X, int wh_splits) {
     const LpgOffsets o = lpg_offsets(X);
     const float* p_wh = ws;
-    const float* p_sm = p_wh + (size_t)WG_SPLITS * LPG_H * LPG_G;
+    const float* p_sm = p_wh + (size_t)WG_SPLITS * LPG_H * LPG_G;   // fixed offsets: the Wh area is sized for the largest split count
     const float* p_em = p_sm + (size_t)SM_SPLITS * SM_TOTAL;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < LPG_H * LPG_G) {
         float v = 0.f;
-        for (int s = 0; s < WG_SPLITS; ++s) v += p_wh[(size_t)s * LPG_H * LPG_G + i];
+        for (int s = 0; s < wh_splits; ++s) v += p_wh[(size_t)s * LPG_H * LPG_G + i];
         grad[o.Wh + i] = v;
         return;
     }
@@ -497,9 +498,29 @@ __global__ void reduce_partials_kernel(const float* __restrict__ ws, float* __re
     }
 }
 
-extern "C" int toued_reduce_partials(const float* workspace, float* grad, int lifetime_conditioning, void* stream) {
+// offsets (in floats) of the three partial areas inside the workspace: {Wh, small, embed}
+extern "C" int toued_lpg_wgrad_workspace_offset(int which) {
+    if (which == 0) return 0;
+    if (which == 1) return WG_SPLITS * LPG_H * LPG_G;
+    return WG_SPLITS * LPG_H * LPG_G + SM_SPLITS * SM_TOTAL;
+}
+
+// embedding-MLP gradients only (shared by the fp32 and the tensor-core reverse pass)
+extern "C" int toued_lpg_wgrad_embed(const int32_t* obs, const uint8_t* done, const float* critic, const float* lpg_params,
+                                     const float* dx, float* workspace, int n_agents, int n_workers, int rollout_len,
+                                     int obs_dim, int lifetime_conditioning, int accumulate, void* stream) {
+    float* p_em = workspace + toued_lpg_wgrad_workspace_offset(2);
+    embed_backward_kernel<<<EM_SPLITS, 256, 0, (cudaStream_t)stream>>>(
+        obs, done, critic, lpg_params, lpg_offsets(lifetime_conditioning ? 7 : 5).e_w0, dx, p_em, n_agents, n_workers,
+        rollout_len, obs_dim, accumulate);
+    TOUED_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int toued_reduce_partials(const float* workspace, float* grad, int lifetime_conditioning, int wh_splits, void* stream) {
     const int n = LPG_H * LPG_G + SM_TOTAL + EM_TOTAL;
-    reduce_partials_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, grad, lifetime_conditioning ? 7 : 5);
+    TOUED_CHECK(wh_splits >= 1 && wh_splits <= WG_SPLITS, "toued_reduce_partials: wh_splits=%d out of range", wh_splits);
+    reduce_partials_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, grad, lifetime_conditioning ? 7 : 5, wh_splits);
     TOUED_LAUNCH_CHECK();
     return 0;
 }

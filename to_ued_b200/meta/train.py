@@ -60,9 +60,12 @@ class MetaGradWorkspace:
         self.whT = torch.empty((768, 256), dtype=f32, device=device)
         self.partials = torch.empty(_lib.lib().toued_lpg_wgrad_workspace_floats(), dtype=f32, device=device)
         self.loss_scal = torch.empty((N, 2), dtype=f32, device=device)
-        if self.tape.precision == "tc":                     # fp32 staging for the (still SIMT) reverse pass
-            self.h32 = torch.empty((L, R, 256), dtype=f32, device=device)
-            self.g32 = torch.empty((4, L, R, 256), dtype=f32, device=device)
+        if self.tape.precision == "tc":
+            Rp = (R + 63) // 64 * 64
+            self.whb_img = torch.empty(256 * 768, dtype=torch.bfloat16, device=device)
+            # bf16 token-tile image of (dar, daz, dhn, dan): 16 column groups of 64
+            self.dgimg = torch.zeros(L * Rp * 1024 * 2, dtype=torch.uint8, device=device)
+        self.off_small = _lib.lib().toued_lpg_wgrad_workspace_offset(1)
         self.key = (N, W, L, obs_dim, K, n_params, str(device))
 
 
@@ -123,7 +126,11 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     gscale = 1.0 / n_global
     bK = [c / K for c in (lpg_hypers.policy_entropy_coeff, lpg_hypers.target_entropy_coeff,
                           lpg_hypers.policy_l2_coeff, lpg_hypers.target_l2_coeff)]
-    _lib.call("toued_transpose_wh", p(lpg), p(ws.whT), s)
+    tc = tape.precision == "tc"
+    if tc:
+        _lib.call("toued_pack_wh_backward", p(lpg), p(ws.whb_img), s)
+    else:
+        _lib.call("toued_transpose_wh", p(lpg), p(ws.whT), s)
 
     new_actor = torch.empty_like(actor.params)
     new_critic = torch.empty_like(critic.params)
@@ -165,17 +172,22 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                       p(ws.d_pi_hat), p(ws.d_y_hat), nb, W, L, D, float(actor.learning_rate),
                       float(critic.learning_rate), float(actor.max_grad_norm),
                       float(lpg_hypers.agent_target_coeff), *[float(b) for b in bK], float(gscale), s)
-            if tape.precision == "tc":
-                ws.h32.copy_(tape.h16[k]); ws.g32.copy_(tape.g16[k])
-                h_k, g_k = ws.h32, ws.g32
-            else:
-                h_k, g_k = tape.h[k], tape.gates[k]
-            _lib.call("toued_gru_backward", p(tape.done[k]), p(lpg), p(ws.whT), p(h_k), p(g_k),
-                      p(tape.y_hat[k]), p(ws.d_pi_hat), p(ws.d_y_hat), p(ws.dl), p(ws.dx), nb, W, L, cond, s)
             first = (mb == 0 and k == K - 1)
-            _lib.call("toued_lpg_wgrad", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg), p(tape.x[k]),
-                      p(h_k), p(g_k), p(ws.d_pi_hat), p(ws.dl), p(ws.dx), p(ws.partials),
-                      nb, W, L, D, cond, 0 if first else 1, s)
+            if tc:
+                _lib.call("toued_gru_backward_tc", p(tape.done[k]), p(lpg), p(ws.whb_img), p(tape.h16[k]),
+                          p(tape.fac[k]), p(tape.y_hat[k]), p(ws.d_pi_hat), p(ws.d_y_hat), p(ws.dgimg), p(ws.dl),
+                          p(ws.dx), nb, W, L, cond, s)
+                _lib.call("toued_lpg_wgrad_tc", p(tape.hpimg[k]), p(ws.dgimg), p(tape.x[k]), p(tape.h16[k]),
+                          p(ws.d_pi_hat), p(ws.dl), p(ws.partials), p(ws.partials[ws.off_small:]),
+                          nb, W, L, 0 if first else 1, s)
+                _lib.call("toued_lpg_wgrad_embed", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg),
+                          p(ws.dx), p(ws.partials), nb, W, L, D, cond, 0 if first else 1, s)
+            else:
+                _lib.call("toued_gru_backward", p(tape.done[k]), p(lpg), p(ws.whT), p(tape.h[k]), p(tape.gates[k]),
+                          p(tape.y_hat[k]), p(ws.d_pi_hat), p(ws.d_y_hat), p(ws.dl), p(ws.dx), nb, W, L, cond, s)
+                _lib.call("toued_lpg_wgrad", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg), p(tape.x[k]),
+                          p(tape.h[k]), p(tape.gates[k]), p(ws.d_pi_hat), p(ws.dl), p(ws.dx), p(ws.partials),
+                          nb, W, L, D, cond, 0 if first else 1, s)
         # ---- metrics (sums over agents; divided by n_global after the all-reduce) ----
         lpg_loss, value_loss = ws.loss_scal[:, 0], ws.loss_scal[:, 1]
         reg = (lpg_loss - lpg_hypers.policy_entropy_coeff * am.policy_entropy + lpg_hypers.policy_l2_coeff * am.policy_l2
@@ -192,7 +204,8 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
         returns[sl] = eval_agent(r_evalagent[sl], rollout_manager, levels, tape.actor[K], eval_workers)
 
     grad = torch.empty(P, dtype=torch.float32, device=dev)
-    _lib.call("toued_reduce_partials", p(ws.partials), p(grad), cond, s)
+    _lib.call("toued_reduce_partials", p(ws.partials), p(grad), cond,
+              _lib.lib().toued_wgrad_tc_splits() if tc else 32, s)
     mvec = torch.cat([msum, returns.sum().view(1)])
     if dist is not None:
         dist.all_reduce(grad)                     # sum of per-rank (1/n_global)-scaled sums = mean
