@@ -144,6 +144,8 @@ def run_ours(a):
     from to_ued_b200.environments.level_sampler import LevelSampler
     from to_ued_b200.meta.meta import create_lpg_train_state, make_lpg_train_step
 
+    import to_ued_b200
+    precision = to_ued_b200.GRU_PRECISION
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -238,6 +240,9 @@ def run_ours(a):
         "toued_gru_forward": tokens * 400896.0,
         "toued_gru_backward": AGENTS_PER_GPU * W * (L - 1) * 2.0 * 768 * 256 + tokens * 2.0 * 256 * 9,
         "toued_lpg_wgrad": tokens * (2.0 * 256 * 768 + 2.0 * 8 * 768 + 2.0 * 256 * 9),
+        "toued_gru_forward_tc": tokens * 400896.0,
+        "toued_gru_backward_tc": AGENTS_PER_GPU * W * (L - 1) * 2.0 * (768 + 2 * 64) * 256 + tokens * 2.0 * 256 * 9,
+        "toued_lpg_wgrad_tc": tokens * (2.0 * 256 * 768 + 2.0 * 8 * 768 + 2.0 * 256 * 9),
     }
     total_prof = sum(ms for _, ms in prof.values()) or 1.0
     shares = {k: {"calls": c, "ms_per_step": ms / a.steps, "share": ms / total_prof} for k, (c, ms) in prof.items()}
@@ -248,7 +253,8 @@ def run_ours(a):
     roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback",
-                "note": "exact-fp32 SIMT GRU path; FLOPs = algorithmic GRU/head/weight-gradient FLOPs per launch"}
+                "note": ("tcgen05 path (fp16/bf16 operands, fp32 accumulate in TMEM)" if precision == "tc" else
+                         "exact-fp32 SIMT GRU path") + "; FLOPs = algorithmic GRU/head/weight-gradient FLOPs per launch"}
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
     cpu = None
@@ -261,11 +267,12 @@ def run_ours(a):
     line = {
         "metric": "gridworld agent env-steps/sec incl. LPG update", "value": value, "unit": "env-steps/s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16/bf16 operands, f32 accumulate (GRU); f32 elsewhere" if precision == "tc" else "f32", "data": "synthetic",
         "config": {"workload": f"LPG meta-gradient step (train.py loop body), env_mode={ENV_MODE}, "
                                f"{AGENTS_PER_GPU} agents/GPU x {W} workers x {L} steps x K={K} updates, "
                                "num_mini_batches=1 (reference README uses 16 as a memory device; results identical)",
-                   "agents_per_gpu": AGENTS_PER_GPU, "global_agents": n_global, "env_steps_per_meta_step": total_env_steps,
+                   "gru_precision": precision, "agents_per_gpu": AGENTS_PER_GPU, "global_agents": n_global, "env_steps_per_meta_step": total_env_steps,
                    "l2_policy": "working set per step (>15 GB of activations) exceeds L2; no explicit flush"},
         "meta_steps_per_s": 1e3 / ms_per_step,
         "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

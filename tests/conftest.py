@@ -18,3 +18,10 @@ def built_lib():
         from to_ued_b200.csrc.build import build
         build()
     return _lib.LIB_PATH
+
+
+@pytest.fixture
+def fp32_gru(monkeypatch):
+    """Run the exact-fp32 SIMT GRU kernels (the tight-tolerance parity tests use these)."""
+    import to_ued_b200
+    monkeypatch.setattr(to_ued_b200, "GRU_PRECISION", "fp32")

@@ -18,7 +18,7 @@ RTOL_LPG = 2e-4       # pi_hat / y_hat after a 20-step fp32 GRU
 
 
 @pytest.mark.parametrize("mode,cond,K", [("all_shortlife", False, 3), ("all_vrandlife", True, 3), ("mazes", False, 2)])
-def test_train_lpg_agent_matches_oracle(built_lib, mode, cond, K):
+def test_train_lpg_agent_matches_oracle(built_lib, fp32_gru, mode, cond, K):
     from to_ued_b200.agents.lpg_agent import train_lpg_agent, Tape
     n = 5
     # agent 1 reaches its lifetime during the K updates (mask path), agent 2 starts beyond it
@@ -30,7 +30,7 @@ def test_train_lpg_agent_matches_oracle(built_lib, mode, cond, K):
     class LS:                       # minimal lpg_train_state
         params = lpg
         class model: lifetime_conditioning = cond
-    tape = Tape(n, c.w, c.L, c.D, K, "cuda")
+    tape = Tape(n, c.w, c.L, c.D, K, "cuda", precision="fp32")
     rng = prng.split(prng.PRNGKey(11), n)
     ag2, rollouts, met = train_lpg_agent(rng, LS, ag, ro, K, 0.5, tape=tape)
     torch.cuda.synchronize()

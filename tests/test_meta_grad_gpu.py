@@ -37,7 +37,7 @@ def _run(c, K, quirk=True, mini_batches=1, n_global=None, offset=0):
 
 @pytest.mark.parametrize("mode,cond,quirk", [("all_shortlife", False, True), ("all_vrandlife", True, True),
                                              ("all_shortlife", False, False)])
-def test_meta_gradient_matches_autograd_oracle(built_lib, mode, cond, quirk):
+def test_meta_gradient_matches_autograd_oracle(built_lib, fp32_gru, mode, cond, quirk):
     K, n = 5, 4
     c = Case(mode, n=n, seed=7, cond=cond, table_scale=0.3, lifetimes=[250, 3, 250, 250], steps=[0, 0, 17, 246])
     (new_ts, ag2, vc2, met), ws = _run(c, K, quirk)
@@ -74,7 +74,7 @@ def test_meta_gradient_matches_autograd_oracle(built_lib, mode, cond, quirk):
     assert torch.equal(vc2.params, Case.pad8(c.value)) and int(vc2.step[0]) == K + 1
 
 
-def test_eval_rollout_and_return_metric_bit_exact(built_lib):
+def test_eval_rollout_and_return_metric_bit_exact(built_lib, fp32_gru):
     """The eval rollout (meta/train.py:46-58) and eval_agent's 4-worker return (Q11) re-sampled by the
     oracle from the CUDA tables."""
     from oracle.agents import eval_agent as o_eval
@@ -90,7 +90,7 @@ def test_eval_rollout_and_return_metric_bit_exact(built_lib):
     np.testing.assert_allclose(float(met["lpg_agent_return"]), float(ret.mean()), rtol=1e-6)
 
 
-def test_mini_batches_and_sharding_are_exact_partitions(built_lib):
+def test_mini_batches_and_sharding_are_exact_partitions(built_lib, fp32_gru):
     """num_mini_batches (util/jax.py:25-41) and the N-way agent partition used for data parallelism
     must not change the result: chunked == full, and sum of per-shard gradients == full."""
     K, n = 2, 4
