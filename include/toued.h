@@ -64,11 +64,13 @@ int toued_sort_tokens(const int32_t* obs, uint16_t* sorted_tok, int n_agents, in
                       int rollout_len, void* stream);
 
 /* lpg_agent.py:46-58 + lpg.py:64-76: actor/critic forward on obs & next_obs, embedding MLP, LPG
- * input rows x f32[L][R][8] = [r, d, pi+1e-8, pyt, pyt1*(1-d), step|0, lifetime|0, 1].            */
+ * input rows x f32[L][R][8] = [r, d, pi+1e-8, pyt, pyt1*(1-d), step|0, lifetime|0, 1].
+ * ximg (or NULL): the same rows as a bf16 token-tile image [L*Rp/64][1][64][64] (zero-initialised by the
+ * caller; columns 8..63 stay zero) for the tensor-core weight-gradient GEMM.                        */
 int toued_lpg_prepare(const int32_t* obs, const uint8_t* action, const float* reward,
                       const uint8_t* done, const float* actor, const float* critic,
                       const float* lpg_params, const int32_t* step, const void* levels, float* x,
-                      int n_agents, int n_workers, int rollout_len, int obs_dim,
+                      void* ximg, int n_agents, int n_workers, int rollout_len, int obs_dim,
                       int lifetime_conditioning, void* stream);
 
 /* lpg.py:11-30,77-84: reverse GRU with done-reset, relu, heads.  Exact-fp32 SIMT path.
@@ -172,8 +174,8 @@ int toued_tc_gemm_mn_test(const float* A, const float* B, void* scratch_img, flo
 int toued_pack_wh_forward(const float* lpg_params, void* wh_img, void* stream);
 /* Tensor-core version of toued_gru_forward (models/lpg.py:11-30,77-84): fp16 operands, fp32
  * accumulation in TMEM.  Saved for the reverse pass (NULL to skip):
- *   h16   f16[L][R][256]      h_t
- *   fac   f16[5][L][R][256]   factors f_r, f_z, f_hn, f_an (d pre-activation = dh * f) and z
+ *   h16   f16, RB32 layout [L][ceil(R/32)][32 chunks][32 rows][8 units] (csrc/tc.cuh::rb32_index)   h_t
+ *   fac   f16[5] planes in the same RB32 layout: factors f_r, f_z, f_hn, f_an (d pre-activation = dh * f) and z
  *   hpimg bf16 token-tile image [L*Rp/64][4][64][64] of the masked carry h' used at each step
  * pi_hat / y_hat stay fp32.                                                                        */
 int toued_gru_forward_tc(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,
@@ -192,7 +194,7 @@ int toued_gru_backward_tc(const uint8_t* done, const float* lpg_params, const vo
 /* Tensor-core weight gradients from the token tile images (hpimg from the forward, dgimg from the
  * backward) + streaming small gradients; partial areas of the toued_lpg_wgrad workspace.             */
 int toued_wgrad_tc_splits(void);
-int toued_lpg_wgrad_tc(const void* hpimg, const void* dgimg, const float* x, const void* h16,
+int toued_lpg_wgrad_tc(const void* hpimg, const void* dgimg, const void* ximg, const void* h16,
                        const float* d_pi_hat, const float* dl, float* wh_partials, float* small_partials,
                        int n_agents, int n_workers, int rollout_len, int accumulate, void* stream);
 

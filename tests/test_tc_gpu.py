@@ -66,12 +66,14 @@ def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond):
         tape.reward[0].copy_(traj.reward); tape.done[0].copy_(traj.done)
         _lib.call("toued_lpg_prepare", p(tape.obs[0]), p(tape.action[0]), p(tape.reward[0]), p(tape.done[0]),
                   p(ag.actor_state.params), p(ag.critic_state.params), p(lpg), p(ag.actor_state.step),
-                  p(ag.level.packed), p(tape.x[0]), n, c.w, c.L, c.D, int(cond), s)
+                  p(ag.level.packed), p(tape.x[0]), None, n, c.w, c.L, c.D, int(cond), s)
         if prec == "tc":
             _lib.call("toued_pack_wh_forward", p(lpg), p(tape.wh_img), s)
             _lib.call("toued_gru_forward_tc", p(tape.x[0]), p(tape.done[0]), p(lpg), p(tape.wh_img), p(tape.h16[0]),
                       p(tape.fac[0]), p(tape.hpimg[0]), p(tape.pi_hat[0]), p(tape.y_hat[0]), n, c.w, c.L, int(cond), s)
-            out[prec] = (tape.pi_hat[0].clone(), tape.y_hat[0].clone(), tape.h16[0].float(), tape.fac[0].float())
+            R = n * c.w
+            out[prec] = (tape.pi_hat[0].clone(), tape.y_hat[0].clone(), _from_rb32(tape.h16[0], c.L, R).float(),
+                         torch.stack([_from_rb32(tape.fac[0][i], c.L, R) for i in range(5)]).float())
             out["hpimg"] = tape.hpimg[0].clone()
         else:
             _lib.call("toued_gru_forward", p(tape.x[0]), p(tape.done[0]), p(lpg), p(tape.h[0]), p(tape.gates[0]),
@@ -145,3 +147,10 @@ def test_meta_gradient_tensor_core_path(built_lib, mode, cond, monkeypatch):
     l2 = np.linalg.norm(g - og) / np.linalg.norm(og)
     print(f"[tc {mode}] relative L2 error of the meta-gradient {l2:.2e}")
     assert l2 < 1e-2
+
+
+def _from_rb32(x, L, R):
+    """RB32 layout [L][R/32][32 chunks][32 rows][8] -> [L][R][256] (inverse of csrc/tc.cuh::rb32_index)."""
+    R32 = (R + 31) // 32
+    v = x.reshape(L, R32, 32, 32, 8).permute(0, 1, 3, 2, 4).reshape(L, R32 * 32, 256)
+    return v[:, :R]

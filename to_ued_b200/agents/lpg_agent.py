@@ -57,10 +57,13 @@ class Tape:
             f16 = torch.float16
             kk = K if keep_gates else 1                      # without a reverse pass one slot is enough
             Rp = (R + 63) // 64 * 64
-            self.h16 = torch.empty((kk, L, R, 256), dtype=f16, device=dev)
-            self.fac = torch.empty((kk, 5, L, R, 256), dtype=f16, device=dev) if keep_gates else None
+            R32 = (R + 31) // 32 * 32                         # RB32 layout pads rows to blocks of 32
+            self.h16 = torch.empty((kk, L, R32, 256), dtype=f16, device=dev)
+            self.fac = torch.empty((kk, 5, L, R32, 256), dtype=f16, device=dev) if keep_gates else None
             # bf16 token-tile image of the masked carry (rows >= R of a partial 64-token block stay zero)
             self.hpimg = torch.zeros((kk, L * Rp * 256 * 2), dtype=torch.uint8, device=dev) if keep_gates else None
+            # bf16 token-tile image of the LPG input rows (one 64-column group; columns 8..63 stay zero)
+            self.ximg = torch.zeros((K, L * Rp * 128), dtype=torch.uint8, device=dev) if keep_gates else None
             self.wh_img = torch.empty(256 * 768, dtype=f16, device=dev)
             self.wh_img_version = None
             self.h = self.gates = None
@@ -88,6 +91,7 @@ def lpg_agent_train_step(k, tape: Tape, levels, step, lpg_params, lifetime_condi
     tape.step_in[k].copy_(step)
     _lib.call("toued_lpg_prepare", p(tape.obs[k]), p(tape.action[k]), p(tape.reward[k]), p(tape.done[k]),
               p(tape.actor[k]), p(tape.critic[k]), p(lpg_params), p(step), p(levels), p(tape.x[k]),
+              p(tape.ximg[k]) if getattr(tape, "ximg", None) is not None else None,
               N, W, L, D, int(lifetime_conditioning), s)
     if tape.precision == "tc":
         ks = k % tape.h16.shape[0]

@@ -151,7 +151,8 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
         const bool rv = row < R;
         const int rsafe = rv ? row : 0;
         const int n_ag = rsafe / W, w_ag = rsafe % W;
-        const size_t gs = (size_t)L * R * LPG_H;
+        const size_t R32 = ((size_t)R + 31) >> 5;
+        const size_t gs = (size_t)L * R32 * 32 * LPG_H;
         const size_t Rp = ((size_t)R + 63) & ~(size_t)63;
         uint32_t ait = 0;
         for (int t = 0; t < L; ++t) {
@@ -197,7 +198,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                         for (int e = 0; e < 8; ++e) carry[e] = 0.f;
                     }
                     float fr[8], fz[8], fhn[8], fan[8], zz[8], hv[8];
-                    const size_t base = tok * LPG_H + u0;
+                    const size_t base = rb32_index((size_t)t, R32, rsafe, u0);
                     unpack8h(*reinterpret_cast<const uint4*>(fac + base), fr);
                     unpack8h(*reinterpret_cast<const uint4*>(fac + gs + base), fz);
                     unpack8h(*reinterpret_cast<const uint4*>(fac + 2 * gs + base), fhn);

@@ -139,7 +139,8 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
         const bool rv = row < R;
         const int rsafe = rv ? row : 0;
         const int n_ag = rsafe / W, w_ag = rsafe % W;
-        const size_t gs = (size_t)L * R * LPG_H;
+        const size_t R32 = ((size_t)R + 31) >> 5;             // 32-row blocks of the RB32 layout
+        const size_t gs = (size_t)L * R32 * 32 * LPG_H;       // elements per saved factor plane
         const size_t Rp = ((size_t)R + 63) & ~(size_t)63;     // rows padded to the 64-token image blocks
         uint32_t it = 0;
         int cur = 0;
@@ -159,7 +160,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
             float head[1 + LPG_Y];
 #pragma unroll
             for (int c = 0; c < 1 + LPG_Y; ++c) head[c] = 0.0f;
-            const size_t tokbase = ((size_t)t * R + rsafe) * LPG_H;
+            const size_t tokbase = rb32_index((size_t)t, R32, rsafe, 0);
             for (int p = 0; p < FT_NPASS; ++p, ++it) {
                 const int a = it & 1;
                 mbar_wait(&acc_full[a], (it >> 1) & 1);
@@ -225,13 +226,14 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                 const uint4 hpk = pack8(hv);
                 *reinterpret_cast<uint4*>(Anxt + soff) = zero_next ? make_uint4(0u, 0u, 0u, 0u) : hpk;
                 if (rv) {
-                    *reinterpret_cast<uint4*>(h16 + tokbase + u0) = hpk;
+                    const size_t so = tokbase + ((size_t)(u0 >> 3) << 8);          // RB32: chunk stride 256 elements
+                    *reinterpret_cast<uint4*>(h16 + so) = hpk;
                     if (fac) {
-                        *reinterpret_cast<uint4*>(fac + tokbase + u0) = pack8(fr);
-                        *reinterpret_cast<uint4*>(fac + gs + tokbase + u0) = pack8(fz);
-                        *reinterpret_cast<uint4*>(fac + 2 * gs + tokbase + u0) = pack8(fhn);
-                        *reinterpret_cast<uint4*>(fac + 3 * gs + tokbase + u0) = pack8(fan);
-                        *reinterpret_cast<uint4*>(fac + 4 * gs + tokbase + u0) = pack8(zz);
+                        *reinterpret_cast<uint4*>(fac + so) = pack8(fr);
+                        *reinterpret_cast<uint4*>(fac + gs + so) = pack8(fz);
+                        *reinterpret_cast<uint4*>(fac + 2 * gs + so) = pack8(fhn);
+                        *reinterpret_cast<uint4*>(fac + 3 * gs + so) = pack8(fan);
+                        *reinterpret_cast<uint4*>(fac + 4 * gs + so) = pack8(zz);
                     }
                     if (hpimg) {
                         // h' consumed at step t-1 (= masked h_t), bf16 token-tile image for the weight-gradient GEMM

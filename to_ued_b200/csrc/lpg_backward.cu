@@ -464,7 +464,7 @@ extern "C" int toued_lpg_wgrad(const int32_t* obs, const uint8_t* done, const fl
 }
 
 // grad = sum over splits of the three partial groups, scattered to the flat parameter layout
-__global__ void reduce_partials_kernel(const float* __restrict__ ws, float* __restrict__ grad, int X, int wh_splits) {
+__global__ void reduce_partials_kernel(const float* __restrict__ ws, float* __restrict__ grad, int X, int wh_splits, int sm_splits) {
     const LpgOffsets o = lpg_offsets(X);
     const float* p_wh = ws;
     const float* p_sm = p_wh + (size_t)WG_SPLITS * LPG_H * LPG_G;   // fixed offsets: the Wh area is sized for the largest split count
@@ -479,7 +479,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ ws, float* __re
     int k = i - LPG_H * LPG_G;
     if (k < SM_TOTAL) {
         float v = 0.f;
-        for (int s = 0; s < SM_SPLITS; ++s) v += p_sm[(size_t)s * SM_TOTAL + k];
+        for (int s = 0; s < sm_splits; ++s) v += p_sm[(size_t)s * SM_TOTAL + k];
         int dst;
         if (k < SM_BHN) { const int q = k / LPG_G, c = k % LPG_G; if (q == 7) dst = o.bi + c; else if (q < X) dst = o.Wi + q * LPG_G + c; else return; }
         else if (k < SM_WPI) dst = o.bhn + (k - SM_BHN);
@@ -520,7 +520,9 @@ extern "C" int toued_lpg_wgrad_embed(const int32_t* obs, const uint8_t* done, co
 extern "C" int toued_reduce_partials(const float* workspace, float* grad, int lifetime_conditioning, int wh_splits, void* stream) {
     const int n = LPG_H * LPG_G + SM_TOTAL + EM_TOTAL;
     TOUED_CHECK(wh_splits >= 1 && wh_splits <= WG_SPLITS, "toued_reduce_partials: wh_splits=%d out of range", wh_splits);
-    reduce_partials_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, grad, lifetime_conditioning ? 7 : 5, wh_splits);
+    // SIMT path: 32 Wh splits / 592 small splits; tensor-core path: 24 / 148
+    const int sm_splits = wh_splits == WG_SPLITS_SIMT ? SM_SPLITS : 148;
+    reduce_partials_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, grad, lifetime_conditioning ? 7 : 5, wh_splits, sm_splits);
     TOUED_LAUNCH_CHECK();
     return 0;
 }

@@ -11,6 +11,7 @@
 //
 // Layouts: trajectory tensors are [n][t][w]; LPG tensors are time-major [t][row], row = n*W + w.
 #include "lpg_common.cuh"
+#include "tc.cuh"
 #include "../../include/toued.h"
 
 // ------------------------------------------------------------------------------------------------
@@ -72,7 +73,7 @@ lpg_prepare_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ 
                    const float* __restrict__ reward, const uint8_t* __restrict__ done,
                    const float* __restrict__ actor, const float* __restrict__ critic,
                    const float* __restrict__ lpg, const int32_t* __restrict__ step,
-                   const LevelRec* __restrict__ levels, float* __restrict__ x,
+                   const LevelRec* __restrict__ levels, float* __restrict__ x, unsigned char* __restrict__ ximg,
                    int n_agents, int W, int L, int D, int cond, int emb_off) {
     __shared__ float sp[LPG_Y * LPG_E + LPG_E + LPG_E + 1];
     for (int i = threadIdx.x; i < LPG_Y * LPG_E + 2 * LPG_E + 1; i += blockDim.x) sp[i] = lpg[emb_off + i];
@@ -105,18 +106,28 @@ lpg_prepare_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ 
     const size_t row = (size_t)n * W + w;
     float4* xo = reinterpret_cast<float4*>(x + ((size_t)t * n_agents * W + row) * LPG_XP);
     xo[0] = make_float4(reward[g], d, pa + 1e-8f, pyt);             // lpg_agent.py:41-43 (pi + 1e-8)
-    xo[1] = make_float4(pyt1, cond ? (float)step[n] : 0.0f, cond ? (float)levels[n].lifetime : 0.0f, 1.0f);
+    const float4 v1 = make_float4(pyt1, cond ? (float)step[n] : 0.0f, cond ? (float)levels[n].lifetime : 0.0f, 1.0f);
+    xo[1] = v1;
+    if (ximg) {      // bf16 token-tile image (one 64-column group, columns 8..63 stay zero) for the weight-gradient GEMM
+        const size_t Rp = ((size_t)n_agents * W + 63) & ~(size_t)63;
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(reward[g], d), b1 = __floats2bfloat162_rn(pa + 1e-8f, pyt);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(v1.x, v1.y), b3 = __floats2bfloat162_rn(v1.z, v1.w);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+        pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+        *reinterpret_cast<uint4*>(ximg + tile_img_offset((size_t)t * Rp + row, 1, 0)) = pk;
+    }
 }
 
 extern "C" int toued_lpg_prepare(const int32_t* obs, const uint8_t* action, const float* reward,
                                  const uint8_t* done, const float* actor, const float* critic,
                                  const float* lpg_params, const int32_t* step, const void* levels,
-                                 float* x, int n_agents, int n_workers, int rollout_len, int obs_dim,
+                                 float* x, void* ximg, int n_agents, int n_workers, int rollout_len, int obs_dim,
                                  int lifetime_conditioning, void* stream) {
     const size_t total = (size_t)n_agents * rollout_len * n_workers;
     TOUED_CHECK(total > 0, "toued_lpg_prepare: empty problem");
     lpg_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        obs, action, reward, done, actor, critic, lpg_params, step, (const LevelRec*)levels, x,
+        obs, action, reward, done, actor, critic, lpg_params, step, (const LevelRec*)levels, x, (unsigned char*)ximg,
         n_agents, n_workers, rollout_len, obs_dim, lifetime_conditioning,
         lpg_offsets(lifetime_conditioning ? 7 : 5).e_w0);
     TOUED_LAUNCH_CHECK();

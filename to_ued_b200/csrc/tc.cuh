@@ -32,6 +32,13 @@ __host__ __device__ __forceinline__ size_t tile_img_offset(size_t tok, int n_col
     return ((tb * n_col_groups + cg) << 13) + (size_t)r * 128 + (size_t)(((cin >> 3) ^ (r & 7)) << 4) + (size_t)((cin & 7) << 1);
 }
 
+// "RB32" layout of per-(token, unit) 16-bit tensors saved between the tensor-core forward and reverse
+// kernels: [t][row block of 32][chunk of 8 units][32 rows][8 units].  A warp of the epilogue (32 rows, one
+// 16-byte chunk each) reads / writes 512 contiguous bytes.  Returns an element (2-byte) index.
+__host__ __device__ __forceinline__ size_t rb32_index(size_t t, size_t n_row_blocks, int row, int u) {
+    return (((t * n_row_blocks + (size_t)(row >> 5)) * 32 + (size_t)(u >> 3)) << 8) + (size_t)((row & 31) << 3) + (size_t)(u & 7);
+}
+
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }

@@ -177,7 +177,7 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                 _lib.call("toued_gru_backward_tc", p(tape.done[k]), p(lpg), p(ws.whb_img), p(tape.h16[k]),
                           p(tape.fac[k]), p(tape.y_hat[k]), p(ws.d_pi_hat), p(ws.d_y_hat), p(ws.dgimg), p(ws.dl),
                           p(ws.dx), nb, W, L, cond, s)
-                _lib.call("toued_lpg_wgrad_tc", p(tape.hpimg[k]), p(ws.dgimg), p(tape.x[k]), p(tape.h16[k]),
+                _lib.call("toued_lpg_wgrad_tc", p(tape.hpimg[k]), p(ws.dgimg), p(tape.ximg[k]), p(tape.h16[k]),
                           p(ws.d_pi_hat), p(ws.dl), p(ws.partials), p(ws.partials[ws.off_small:]),
                           nb, W, L, 0 if first else 1, s)
                 _lib.call("toued_lpg_wgrad_embed", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg),
