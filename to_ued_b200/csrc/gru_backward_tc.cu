@@ -68,8 +68,8 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
     unsigned char* sI = sB + BT_NSB * BT_BCHUNK;                // 8 KB identity
     float* swp = reinterpret_cast<float*>(sI + BT_ICHUNK);      // [256]
     float* sWy = swp + LPG_H;                                   // [256][8]
-    float* sWi = sWy + LPG_H * LPG_Y;                           // [2][768] rows 3, 4 of Wi
-    float* sdx = sWi + 2 * LPG_G;                               // [128][2]
+    float* sWi = sWy + LPG_H * LPG_Y;                           // [256 units][8]: Wi rows 3, 4 x gates (r, z, n), 2 pad
+    float* sdx = sWi + LPG_H * 8;                               // [128][2]
     __shared__ __align__(8) uint64_t b_full[BT_NSB], b_empty[BT_NSB], a_full, a_empty, q_full;
     __shared__ uint32_t tmem_base_s;
 
@@ -85,7 +85,10 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
     if (warp == 9) tmem_alloc(&tmem_base_s, 512);
     for (int i = tid; i < LPG_H; i += BT_THREADS) swp[i] = lpg[o.w_pi + i];
     for (int i = tid; i < LPG_H * LPG_Y; i += BT_THREADS) sWy[i] = lpg[o.W_y + i];
-    for (int i = tid; i < 2 * LPG_G; i += BT_THREADS) sWi[i] = lpg[o.Wi + 3 * LPG_G + i];
+    for (int i = tid; i < LPG_H * 8; i += BT_THREADS) {
+        const int u = i >> 3, q = i & 7;               // q = 3 * (input row - 3) + gate
+        sWi[i] = q < 6 ? lpg[o.Wi + (3 + q / 3) * LPG_G + (q % 3) * LPG_H + u] : 0.0f;
+    }
     for (int i = tid; i < 64 * 64; i += BT_THREADS) {
         const int n = i >> 6, k = i & 63;
         *reinterpret_cast<__nv_bfloat16*>(sI + sw128_offset(64, n, k)) = __float2bfloat16_rn(n == k ? 1.0f : 0.0f);
@@ -210,19 +213,23 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                     for (int e = 0; e < 8; ++e) {
                         const int u = u0 + e;
                         float dh = nd * carry[e];
-                        if (hv[e] > 0.0f) {
+                        {
+                            const float4 w0 = *reinterpret_cast<const float4*>(sWy + u * 8), w1 = *reinterpret_cast<const float4*>(sWy + u * 8 + 4);
                             float hd = dpi * swp[u];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) hd = fmaf(dl[i], sWy[u * 8 + i], hd);
-                            dh += hd;
+                            hd = fmaf(dl[0], w0.x, hd); hd = fmaf(dl[1], w0.y, hd); hd = fmaf(dl[2], w0.z, hd); hd = fmaf(dl[3], w0.w, hd);
+                            hd = fmaf(dl[4], w1.x, hd); hd = fmaf(dl[5], w1.y, hd); hd = fmaf(dl[6], w1.z, hd); hd = fmaf(dl[7], w1.w, hd);
+                            dh += hv[e] > 0.0f ? hd : 0.0f;
                         }
                         if (!rv) dh = 0.0f;
                         gr[e] = dh * fr[e]; gz[e] = dh * fz[e]; ghn[e] = dh * fhn[e]; gan[e] = dh * fan[e];
                         const float cz = dh * zz[e];
                         czh[e] = __bfloat162float(__float2bfloat16_rn(cz));
                         czl[e] = cz - czh[e];
-                        dx3 = fmaf(gr[e], sWi[u], fmaf(gz[e], sWi[LPG_H + u], fmaf(gan[e], sWi[2 * LPG_H + u], dx3)));
-                        dx4 = fmaf(gr[e], sWi[LPG_G + u], fmaf(gz[e], sWi[LPG_G + LPG_H + u], fmaf(gan[e], sWi[LPG_G + 2 * LPG_H + u], dx4)));
+                        {
+                            const float4 w0 = *reinterpret_cast<const float4*>(sWi + u * 8), w1 = *reinterpret_cast<const float4*>(sWi + u * 8 + 4);
+                            dx3 = fmaf(gr[e], w0.x, fmaf(gz[e], w0.y, fmaf(gan[e], w0.z, dx3)));
+                            dx4 = fmaf(gr[e], w0.w, fmaf(gz[e], w1.x, fmaf(gan[e], w1.y, dx4)));
+                        }
                     }
                     outA[0][c8] = pack8bf(gr); outA[1][c8] = pack8bf(gz); outA[2][c8] = pack8bf(ghn);
                     outA[3][c8] = pack8bf(czh); outA[4][c8] = pack8bf(czl);
@@ -263,7 +270,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
 }
 
 static size_t gru_bwd_tc_smem() {
-    return BT_ASTAGE + BT_NSB * BT_BCHUNK + BT_ICHUNK + sizeof(float) * (LPG_H + LPG_H * LPG_Y + 2 * LPG_G + BT_M * 2) + 1024;
+    return BT_ASTAGE + BT_NSB * BT_BCHUNK + BT_ICHUNK + sizeof(float) * (LPG_H + LPG_H * LPG_Y + LPG_H * 8 + BT_M * 2) + 1024;
 }
 
 extern "C" int toued_gru_backward_tc(const uint8_t* done, const float* lpg_params, const void* whb_img,

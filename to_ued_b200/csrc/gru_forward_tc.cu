@@ -55,9 +55,8 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sA = smem;                                   // 2 x 64 KB
     unsigned char* sB = sA + 2 * FT_ABUF;                       // FT_NS x 24 KB
-    float* sWi = reinterpret_cast<float*>(sB + FT_NS * FT_BSTAGE);   // [X][768]
-    float* sbi = sWi + X * LPG_G;                               // [768]
-    float* sbhn = sbi + LPG_G;                                  // [256]
+    float* sWi = reinterpret_cast<float*>(sB + FT_NS * FT_BSTAGE);   // [256 units][3 gates][8]: Wi rows 0..X-1, 0.., bias in slot 7
+    float* sbhn = sWi + LPG_H * 24;                             // [256]
     float* swp = sbhn + LPG_H;                                  // [256]
     float* sWy = swp + LPG_H;                                   // [256][8]
     float* shead = sWy + LPG_H * LPG_Y;                         // [128][9] partial heads of the hf=1 half
@@ -75,8 +74,10 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
         mbar_fence_init();
     }
     if (warp == 9) tmem_alloc(&tmem_base_s, 128);
-    for (int i = tid; i < X * LPG_G; i += FT_THREADS) sWi[i] = lpg[o.Wi + i];
-    for (int i = tid; i < LPG_G; i += FT_THREADS) sbi[i] = lpg[o.bi + i];
+    for (int i = tid; i < LPG_H * 24; i += FT_THREADS) {
+        const int u = i / 24, g = (i % 24) >> 3, q = i & 7;
+        sWi[i] = q < X ? lpg[o.Wi + q * LPG_G + g * LPG_H + u] : (q == 7 ? lpg[o.bi + g * LPG_H + u] : 0.0f);
+    }
     for (int i = tid; i < LPG_H; i += FT_THREADS) { sbhn[i] = lpg[o.bhn + i]; swp[i] = lpg[o.w_pi + i]; }
     for (int i = tid; i < LPG_H * LPG_Y; i += FT_THREADS) sWy[i] = lpg[o.W_y + i];
     // initial carry = 0 (both A buffers)
@@ -145,13 +146,13 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
         uint32_t it = 0;
         int cur = 0;
         for (int t = L - 1; t >= 0; --t) {
-            float xr[X];
+            float xr[8];                                       // x row; slot 7 is the constant 1 (bias)
             {
                 const float4* xp = reinterpret_cast<const float4*>(x + ((size_t)t * R + rsafe) * LPG_XP);
                 const float4 x0 = xp[0], x1 = xp[1];
                 const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-                for (int i = 0; i < X; ++i) xr[i] = rv ? xa[i] : 0.0f;
+                for (int i = 0; i < 8; ++i) xr[i] = rv ? xa[i] : 0.0f;
             }
             // mask for the NEXT processed step (t-1): its carry is zero where done[t-1]
             const bool zero_next = (t > 0) && done[((size_t)n_ag * L + (t - 1)) * W + w_ag];
@@ -185,17 +186,26 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int u = u0 + e;
-                    float gr = sbi[u], gz = sbi[LPG_H + u], gn = sbi[2 * LPG_H + u];
-#pragma unroll
-                    for (int i = 0; i < X; ++i) {
-                        gr = fmaf(xr[i], sWi[i * LPG_G + u], gr);
-                        gz = fmaf(xr[i], sWi[i * LPG_G + LPG_H + u], gz);
-                        gn = fmaf(xr[i], sWi[i * LPG_G + 2 * LPG_H + u], gn);
+                    float gr = ar[e], gz = az[e], gn = 0.0f;
+                    {
+                        const float4* wv = reinterpret_cast<const float4*>(sWi + u * 24);     // warp-broadcast loads
+                        const float4 r0 = wv[0], r1 = wv[1], z0 = wv[2], z1 = wv[3], n0 = wv[4], n1 = wv[5];
+                        gr = fmaf(xr[0], r0.x, gr); gr = fmaf(xr[1], r0.y, gr); gr = fmaf(xr[2], r0.z, gr); gr = fmaf(xr[3], r0.w, gr);
+                        gr = fmaf(xr[4], r1.x, gr); gr = fmaf(xr[7], r1.w, gr);
+                        gz = fmaf(xr[0], z0.x, gz); gz = fmaf(xr[1], z0.y, gz); gz = fmaf(xr[2], z0.z, gz); gz = fmaf(xr[3], z0.w, gz);
+                        gz = fmaf(xr[4], z1.x, gz); gz = fmaf(xr[7], z1.w, gz);
+                        gn = fmaf(xr[0], n0.x, gn); gn = fmaf(xr[1], n0.y, gn); gn = fmaf(xr[2], n0.z, gn); gn = fmaf(xr[3], n0.w, gn);
+                        gn = fmaf(xr[4], n1.x, gn); gn = fmaf(xr[7], n1.w, gn);
+                        if (X > 5) {
+                            gr = fmaf(xr[5], r1.y, gr); gr = fmaf(xr[6], r1.z, gr);
+                            gz = fmaf(xr[5], z1.y, gz); gz = fmaf(xr[6], z1.z, gz);
+                            gn = fmaf(xr[5], n1.y, gn); gn = fmaf(xr[6], n1.z, gn);
+                        }
                     }
-                    const float rr = sigmoidf_(gr + ar[e]);
-                    zz[e] = sigmoidf_(gz + az[e]);
+                    const float rr = sigmoid_fast(gr);
+                    zz[e] = sigmoid_fast(gz);
                     const float hn = an[e] + sbhn[u];
-                    const float nn = tanhf_(gn + rr * hn);
+                    const float nn = tanh_fast(gn + rr * hn);
                     hv[e] = (1.0f - zz[e]) * nn + zz[e] * hp[e];
                     // reverse-pass factors: d(pre-activation) = dh * factor   (lpg.py GRUCell backward)
                     fan[e] = (1.0f - zz[e]) * (1.0f - nn * nn);          // dan = dh * fan
@@ -204,8 +214,11 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                     fz[e] = (hp[e] - nn) * zz[e] * (1.0f - zz[e]);        // daz
                     const float y = fmaxf(hv[e], 0.0f);
                     head[0] = fmaf(y, swp[u], head[0]);
-#pragma unroll
-                    for (int c = 0; c < LPG_Y; ++c) head[1 + c] = fmaf(y, sWy[u * LPG_Y + c], head[1 + c]);
+                    {
+                        const float4 w0 = *reinterpret_cast<const float4*>(sWy + u * LPG_Y), w1 = *reinterpret_cast<const float4*>(sWy + u * LPG_Y + 4);
+                        head[1] = fmaf(y, w0.x, head[1]); head[2] = fmaf(y, w0.y, head[2]); head[3] = fmaf(y, w0.z, head[3]); head[4] = fmaf(y, w0.w, head[4]);
+                        head[5] = fmaf(y, w1.x, head[5]); head[6] = fmaf(y, w1.y, head[6]); head[7] = fmaf(y, w1.z, head[7]); head[8] = fmaf(y, w1.w, head[8]);
+                    }
                 }
                 auto pack8 = [](const float (&v)[8]) {
                     uint4 r;
@@ -277,7 +290,8 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
 }
 
 static size_t gru_fwd_tc_smem(int X) {
-    return 2 * FT_ABUF + FT_NS * FT_BSTAGE + sizeof(float) * (X * LPG_G + LPG_G + 2 * LPG_H + LPG_H * LPG_Y + FT_M * 9) + 1024;
+    (void)X;
+    return 2 * FT_ABUF + FT_NS * FT_BSTAGE + sizeof(float) * (LPG_H * 24 + 2 * LPG_H + LPG_H * LPG_Y + FT_M * 9) + 1024;
 }
 
 extern "C" int toued_gru_forward_tc(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,

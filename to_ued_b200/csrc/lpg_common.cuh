@@ -41,6 +41,11 @@ __device__ __forceinline__ float tanhf_(float x) {
     return 1.0f - 2.0f / (e + 1.0f);
 }
 
+// fast variants for the tensor-core epilogues (MUFU.EX2 + MUFU.RCP, ~2 ulp): the operands there are
+// fp16/bf16-rounded anyway
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
+
 // softmax over C values (true expf; float path, tolerance-checked)
 template <int C>
 __device__ __forceinline__ void softmax_c(const float (&z)[C], float (&p)[C]) {
