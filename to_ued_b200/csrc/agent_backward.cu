@@ -18,11 +18,8 @@
 //
 // Every row scatter is a segmented sum over the row-sorted token list: deterministic, no atomics.
 #include "lpg_common.cuh"
+#include "segreduce.cuh"
 #include "../../include/toued.h"
-
-__device__ __forceinline__ bool seg_head(const uint16_t* st, const int32_t* ob, int i) {
-    return i == 0 || ob_idx(ob[st[i - 1]]) != ob_idx(ob[st[i]]);
-}
 
 // ------------------------------------------------------------------------------------------------
 // meta loss on the eval rollout + lam_K
@@ -38,7 +35,12 @@ meta_loss_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ ac
     float* rec = adv + L * W;              // [T][6]: 5 dlogits + tf
     float* abar = rec + L * W * 6;         // [W]
     float* lbar = abar + W;                // [W]
+    float* runv = lbar + W;                // [T][5]
+    float* scan = runv + L * W * 5;        // [2][256][5]
+    void* idxmem = scan + 2 * 256 * 5;
     __shared__ float red[32];
+    __shared__ int iscan[512];
+    __shared__ unsigned char sflags[512];
     const int n = blockIdx.x, tid = threadIdx.x, T = W * L;
     const int32_t* ob = obs + (size_t)n * (L + 1) * W;
     const uint8_t* act = action + (size_t)n * T;
@@ -50,6 +52,7 @@ meta_loss_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ ac
     float* lm = lam + (size_t)n * D * 8;
     float* mm = mu + (size_t)n * D * 8;
     const float invT = 1.0f / (float)T;
+    const SegIndex si = seg_index_build(idxmem, iscan, st, ob, T);
 
     for (int i = tid; i < D * 2; i += 256) {
         reinterpret_cast<float4*>(lm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -123,18 +126,11 @@ meta_loss_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ ac
 #pragma unroll
     for (int j = 0; j < 5; ++j) last[j] = block_sum(last[j], red);
     __syncthreads();
-    for (int i = tid; i < T; i += 256) {
-        if (!seg_head(st, ob, i)) continue;
-        const int row = ob_idx(ob[st[i]]);
-        float g[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int q = i; q < T; ++q) {
-            const int tk = st[q];
-            if (ob_idx(ob[tk]) != row) break;
+    seg_reduce<5, 6>(rec, si, T, runv, scan, sflags);
+    for (int r = tid; r < si.nruns; r += 256) {
+        const int row = si.run_row[r];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) g[j] += rec[tk * 6 + j];
-        }
-#pragma unroll
-        for (int j = 0; j < 5; ++j) lm[(size_t)row * 8 + j] = g[j];
+        for (int j = 0; j < 5; ++j) lm[(size_t)row * 8 + j] = runv[r * 5 + j];
     }
     if (tid == 0) {
 #pragma unroll
@@ -151,7 +147,7 @@ extern "C" int toued_meta_loss(const int32_t* obs, const uint8_t* action, const 
                                float gae_lambda, float grad_scale, int outer_product_quirk, void* stream) {
     const int T = n_workers * rollout_len;
     TOUED_CHECK(n_agents > 0 && T > 0, "toued_meta_loss: empty problem");
-    const size_t smem = sizeof(float) * ((size_t)T * 7 + 2 * n_workers);
+    const size_t smem = sizeof(float) * ((size_t)T * 7 + 2 * n_workers + (size_t)T * 5 + 2 * 256 * 5) + seg_index_bytes(T);
     TOUED_CHECK(smem <= 200 * 1024, "toued_meta_loss: W*L=%d too large for shared memory", T);
     TOUED_CUDA(cudaFuncSetAttribute(meta_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     meta_loss_kernel<<<n_agents, 256, smem, (cudaStream_t)stream>>>(
@@ -211,9 +207,11 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
                       float* lam, float* mu, float* __restrict__ d_pi_hat, float* __restrict__ d_y_hat,
                       int n_agents, int W, int L, int D, float lr_a, float lr_c, float max_norm,
                       float alpha, float b_pent, float b_yent, float b_pl2, float b_yl2, float gscale) {
-    extern __shared__ __align__(16) float rec[];       // [T][14]
+    extern __shared__ __align__(16) float rec[];       // [T][14] records | [T][13] run vectors | scan | index
     __shared__ float red[32];
     __shared__ float s_wlast[13];
+    __shared__ int iscan[512];
+    __shared__ unsigned char sflags[512];
     const int n = blockIdx.x, tid = threadIdx.x, T = W * L, R = n_agents * W;
     const int32_t* ob = obs + (size_t)n * (L + 1) * W;
     const uint8_t* act = action + (size_t)n * T;
@@ -227,6 +225,9 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
     const float invT = 1.0f / (float)T;
     const float gna = upd_scal[n * 8 + 0], gnc = upd_scal[n * 8 + 1];
     const bool keep = upd_scal[n * 8 + 2] != 0.0f;
+    float* runv = rec + (size_t)T * 14;
+    float* scan = runv + (size_t)T * 13;
+    const SegIndex si = seg_index_build(scan + 2 * 256 * 13, iscan, st, ob, T);
 
     // ---- A. entropy regularisers evaluated at the UPDATED tables (lpg_agent.py:119-120) -------
     // L has  -b_pent/K * H(pi_{theta_{k+1}})  and  -b_yent/K * H(y_{phi_{k+1}})   (1/K folded into b_*)
@@ -259,18 +260,10 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
 #pragma unroll
     for (int j = 0; j < 13; ++j) last[j] = block_sum(last[j], red);
     __syncthreads();
-    for (int i = tid; i < T; i += 256) {
-        if (!seg_head(st, ob, i)) continue;
-        const int row = ob_idx(ob[st[i]]);
-        float g[13];
-#pragma unroll
-        for (int j = 0; j < 13; ++j) g[j] = 0.f;
-        for (int q = i; q < T; ++q) {
-            const int tk = st[q];
-            if (ob_idx(ob[tk]) != row) break;
-#pragma unroll
-            for (int j = 0; j < 13; ++j) g[j] += rec[tk * 14 + j];
-        }
+    seg_reduce<13, 14>(rec, si, T, runv, scan, sflags);
+    for (int r = tid; r < si.nruns; r += 256) {
+        const int row = si.run_row[r];
+        const float* g = runv + r * 13;
 #pragma unroll
         for (int j = 0; j < 5; ++j) lm[(size_t)row * 8 + j] += g[j];
 #pragma unroll
@@ -317,19 +310,11 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
     for (int j = 0; j < 13; ++j) last[j] = block_sum(last[j], red);     // g_k[D-1]
     __syncthreads();
     // ---- B2. <g_k, lam>, <g_k^c, mu> ------------------------------------------------------------
+    seg_reduce<13, 14>(rec, si, T, runv, scan, sflags);           // g_k rows
     float dot_a = 0.f, dot_c = 0.f;
-    for (int i = tid; i < T; i += 256) {
-        if (!seg_head(st, ob, i)) continue;
-        const int row = ob_idx(ob[st[i]]);
-        float g[13];
-#pragma unroll
-        for (int j = 0; j < 13; ++j) g[j] = 0.f;
-        for (int q = i; q < T; ++q) {
-            const int tk = st[q];
-            if (ob_idx(ob[tk]) != row) break;
-#pragma unroll
-            for (int j = 0; j < 13; ++j) g[j] += rec[tk * 14 + j];
-        }
+    for (int r = tid; r < si.nruns; r += 256) {
+        const int row = si.run_row[r];
+        const float* g = runv + r * 13;
         float l8[8], m8[8];
         load8(lm + (size_t)row * 8, l8); load8(mm + (size_t)row * 8, m8);
 #pragma unroll
@@ -359,48 +344,34 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
 #pragma unroll
     for (int j = 0; j < 13; ++j) wl[j] = s_wlast[j];
 
-    // ---- B3a. per row segment: w_row = k * (lam_row - proj * g_row), broadcast into the records of
-    //           the segment's tokens (their forward-gradient records are no longer needed) ----------
-    for (int i = tid; i < T; i += 256) {
-        if (!seg_head(st, ob, i)) continue;
-        const int row = ob_idx(ob[st[i]]);
-        float g[13];
-#pragma unroll
-        for (int j = 0; j < 13; ++j) g[j] = 0.f;
-        int qe = i;
-        for (; qe < T; ++qe) {
-            const int tk = st[qe];
-            if (ob_idx(ob[tk]) != row) break;
-#pragma unroll
-            for (int j = 0; j < 13; ++j) g[j] += rec[tk * 14 + j];
-        }
-        float l8[8], m8[8], wr[13];
+    // ---- B3a. per row: w_row = k * (lam_row - proj * g_row), kept as the run's vector -----------------
+    for (int r = tid; r < si.nruns; r += 256) {
+        const int row = si.run_row[r];
+        float* g = runv + r * 13;
+        float l8[8], m8[8];
         load8(lm + (size_t)row * 8, l8); load8(mm + (size_t)row * 8, m8);
 #pragma unroll
-        for (int j = 0; j < 5; ++j) wr[j] = ka * (l8[j] - pa_ * g[j]);
+        for (int j = 0; j < 5; ++j) g[j] = ka * (l8[j] - pa_ * g[j]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) wr[5 + j] = kc * (m8[j] - pc_ * g[5 + j]);
-        for (int q = i; q < qe; ++q) {
-            float* r = rec + st[q] * 14;
-#pragma unroll
-            for (int j = 0; j < 13; ++j) r[j] = wr[j];
-        }
+        for (int j = 0; j < 8; ++j) g[5 + j] = kc * (m8[j] - pc_ * g[5 + j]);
     }
     __syncthreads();
     // ---- B3b. token-parallel: cotangents of pi_hat / y_hat and the Hessian-vector contributions ----
     float hl[13];
 #pragma unroll
     for (int j = 0; j < 13; ++j) hl[j] = 0.f;
-    for (int tok = tid; tok < T; tok += 256) {
+    for (int pos = tid; pos < T; pos += 256) {
+        const int tok = si.tok[pos];
         const int t = tok / W, w = tok - t * W;
         const size_t li = (size_t)t * R + (size_t)n * W + w;
         const TokFwd f = tok_forward(a0, c0, D, ob[tok], act[tok]);
         const float ph = pi_hat[li];
         float yh[8]; load8(y_hat + li * 8, yh);
         float* r = rec + tok * 14;
+        const float* wr = runv + (size_t)si.run[pos] * 13;
         float v[13];
 #pragma unroll
-        for (int j = 0; j < 13; ++j) v[j] = fmaf(f.tf, wl[j], r[j]);
+        for (int j = 0; j < 13; ++j) v[j] = fmaf(f.tf, wl[j], wr[j]);
         // actor:  S = q * (v_a - p.v)
         float va = v[0], pv = 0.f;
 #pragma unroll
@@ -446,22 +417,14 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
     for (int j = 0; j < 13; ++j) hl[j] = block_sum(hl[j], red);
     __syncthreads();
     // ---- B3c. segmented sums of the HVP contributions into lam_k / mu_k --------------------------
-    for (int i = tid; i < T; i += 256) {
-        if (!seg_head(st, ob, i)) continue;
-        const int row = ob_idx(ob[st[i]]);
-        float hr[13];
+    seg_reduce<13, 14>(rec, si, T, runv, scan, sflags);
+    for (int r = tid; r < si.nruns; r += 256) {
+        const int row = si.run_row[r];
+        const float* g = runv + r * 13;
 #pragma unroll
-        for (int j = 0; j < 13; ++j) hr[j] = 0.f;
-        for (int q = i; q < T; ++q) {
-            const int tk = st[q];
-            if (ob_idx(ob[tk]) != row) break;
+        for (int j = 0; j < 5; ++j) lm[(size_t)row * 8 + j] += g[j];
 #pragma unroll
-            for (int j = 0; j < 13; ++j) hr[j] += rec[tk * 14 + j];
-        }
-#pragma unroll
-        for (int j = 0; j < 5; ++j) lm[(size_t)row * 8 + j] += hr[j];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) mm[(size_t)row * 8 + j] += hr[5 + j];
+        for (int j = 0; j < 8; ++j) mm[(size_t)row * 8 + j] += g[5 + j];
     }
     if (tid == 0) {
 #pragma unroll
@@ -482,7 +445,7 @@ extern "C" int toued_agent_backward(const int32_t* obs, const uint8_t* action, c
                                     float grad_scale, void* stream) {
     const int T = n_workers * rollout_len;
     TOUED_CHECK(n_agents > 0 && T > 0, "toued_agent_backward: empty problem");
-    const size_t smem = (size_t)T * 14 * sizeof(float);
+    const size_t smem = sizeof(float) * ((size_t)T * 14 + (size_t)T * 13 + 2 * 256 * 13) + seg_index_bytes(T);
     TOUED_CHECK(smem <= 200 * 1024, "toued_agent_backward: W*L=%d too large for shared memory", T);
     TOUED_CUDA(cudaFuncSetAttribute(agent_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     agent_backward_kernel<<<n_agents, 256, smem, (cudaStream_t)stream>>>(

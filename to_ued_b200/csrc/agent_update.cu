@@ -10,9 +10,10 @@
 // observation row and the time row D-1), so the gradient is closed-form and sparse:
 //   actor : dlogit_j = (1/T) * pi_hat * p_a/(p_a+1e-8) * (delta_aj - p_j)
 //   critic: dlogit_i = (alpha/T) * y_i * (m_i - sum_j y_j m_j),  m = log(y+e) - log(y_hat+e) + y/(y+e)
-// Row sums are segmented sums over the agent's row-sorted token list (toued_sort_tokens), each
-// segment accumulated sequentially by one thread: bitwise deterministic, no atomics.
+// Row sums are segmented sums over the agent's row-sorted token list (toued_sort_tokens), computed by
+// the fixed-tree block reduction of segreduce.cuh: bitwise deterministic, no atomics.
 #include "lpg_common.cuh"
+#include "segreduce.cuh"
 #include "../../include/toued.h"
 
 constexpr int AU_C = 14;   // per-token record: 5 actor dlogits, 8 critic dlogits, tf
@@ -25,17 +26,22 @@ agent_update_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__
                     const LevelRec* __restrict__ levels, int32_t* __restrict__ step,
                     float* __restrict__ scal, int n_agents, int W, int L, int D,
                     float lr_a, float lr_c, float max_norm, float alpha) {
-    extern __shared__ __align__(16) float smc[];          // [T][AU_C]
+    extern __shared__ __align__(16) float smc[];          // [T][AU_C] records | [T][13] run sums | scan | index
     __shared__ float red[32];
+    __shared__ int iscan[512];
+    __shared__ unsigned char sflags[512];
     const int n = blockIdx.x, tid = threadIdx.x, T = W * L, R = n_agents * W;
+    float* runv = smc + (size_t)T * AU_C;
+    float* scan = runv + (size_t)T * 13;
+    void* idxmem = scan + 2 * 256 * 13;
     const int32_t* ob = obs + (size_t)n * (L + 1) * W;
     const uint8_t* act = action + (size_t)n * T;
-    const uint16_t* st = sorted_tok + (size_t)n * T;
     const float* a_in = actor_in + (size_t)n * D * 8;
     const float* c_in = critic_in + (size_t)n * D * 8;
     float* a_out = actor_out + (size_t)n * D * 8;
     float* c_out = critic_out + (size_t)n * D * 8;
     const float invT = 1.0f / (float)T;
+    const SegIndex si = seg_index_build(idxmem, iscan, sorted_tok + (size_t)n * T, ob, T);
 
     // dense copy theta_k -> theta_{k+1} (only touched rows change below)
     for (int i = tid; i < D * 2; i += 256) {
@@ -93,22 +99,11 @@ agent_update_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__
     m_kl = block_sum(m_kl, red); m_pi2 = block_sum(m_pi2, red); m_y2 = block_sum(m_y2, red);
     __syncthreads();
 
-    // ---- phase 1: squared gradient norms over row segments -------------------------------
+    // ---- phase 1: row gradients (segmented sums) and their squared norms --------------------------
+    seg_reduce<13, AU_C>(smc, si, T, runv, scan, sflags);
     float na = 0.f, nc = 0.f;
-    for (int i = tid; i < T; i += 256) {
-        const int tok = st[i];
-        const int row = ob_idx(ob[tok]);
-        if (i > 0 && ob_idx(ob[st[i - 1]]) == row) continue;        // not a segment head
-        float g[13];
-#pragma unroll
-        for (int j = 0; j < 13; ++j) g[j] = 0.f;
-        for (int q = i; q < T; ++q) {
-            const int tk = st[q];
-            if (ob_idx(ob[tk]) != row) break;
-            const float* rec = smc + tk * AU_C;
-#pragma unroll
-            for (int j = 0; j < 13; ++j) g[j] += rec[j];
-        }
+    for (int r = tid; r < si.nruns; r += 256) {
+        const float* g = runv + r * 13;
 #pragma unroll
         for (int j = 0; j < 5; ++j) na = fmaf(g[j], g[j], na);
 #pragma unroll
@@ -126,23 +121,11 @@ agent_update_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__
     const int old_step = step[n];
     const bool keep = (old_step + 1) <= levels[n].lifetime;          // lpg_agent.py:78-82
     const float ua = keep ? lr_a * sa : 0.0f, uc = keep ? lr_c * sc : 0.0f;
-    __syncthreads();
 
     // ---- phase 2: SGD on the touched rows ---------------------------------------------------
-    for (int i = tid; i < T; i += 256) {
-        const int tok = st[i];
-        const int row = ob_idx(ob[tok]);
-        if (i > 0 && ob_idx(ob[st[i - 1]]) == row) continue;
-        float g[13];
-#pragma unroll
-        for (int j = 0; j < 13; ++j) g[j] = 0.f;
-        for (int q = i; q < T; ++q) {
-            const int tk = st[q];
-            if (ob_idx(ob[tk]) != row) break;
-            const float* rec = smc + tk * AU_C;
-#pragma unroll
-            for (int j = 0; j < 13; ++j) g[j] += rec[j];
-        }
+    for (int r = tid; r < si.nruns; r += 256) {
+        const int row = si.run_row[r];
+        const float* g = runv + r * 13;
 #pragma unroll
         for (int j = 0; j < 5; ++j) a_out[(size_t)row * 8 + j] = a_in[(size_t)row * 8 + j] - ua * g[j];
 #pragma unroll
@@ -183,6 +166,10 @@ agent_update_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__
     }
 }
 
+static size_t agent_smem_bytes(int T) {
+    return sizeof(float) * ((size_t)T * AU_C + (size_t)T * 13 + 2 * 256 * 13) + seg_index_bytes(T);
+}
+
 extern "C" int toued_agent_update(const int32_t* obs, const uint8_t* action, const uint16_t* sorted_tok,
                                   const float* pi_hat, const float* y_hat, const float* actor_in,
                                   const float* critic_in, float* actor_out, float* critic_out,
@@ -190,7 +177,7 @@ extern "C" int toued_agent_update(const int32_t* obs, const uint8_t* action, con
                                   int n_workers, int rollout_len, int obs_dim, float lr_actor,
                                   float lr_critic, float max_grad_norm, float agent_target_coeff, void* stream) {
     const int T = n_workers * rollout_len;
-    const size_t smem = (size_t)T * AU_C * sizeof(float);
+    const size_t smem = agent_smem_bytes(T);
     TOUED_CHECK(n_agents > 0 && T > 0, "toued_agent_update: empty problem");
     TOUED_CHECK(smem <= 200 * 1024, "toued_agent_update: W*L=%d too large for shared memory", T);
     TOUED_CHECK(actor_in != actor_out && critic_in != critic_out, "toued_agent_update: in-place update not supported");
