@@ -74,6 +74,7 @@ def run_reference(a):
         return
     from to_ued_b200.experiments.parse_args import parse_args
     args = parse_args(["--env_mode", ENV_MODE])
+    torch.set_num_threads(os.cpu_count() or 1)          # torchrun pins OMP_NUM_THREADS=1; use every host core
     cores = torch.get_num_threads()
     for _ in range(a.warmup):
         cpu_reference_step(2)

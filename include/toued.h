@@ -149,6 +149,16 @@ int toued_reduce_partials(const float* workspace, float* grad, int lifetime_cond
 int toued_adam(float* params, const float* grad, float* mu, float* nu, int n, int count, float lr,
                float b1, float b2, float eps, void* stream);
 
+/* ---- A2C antagonist (agents/a2c.py:19-76), used by the algorithmic-regret level score ---------- */
+/* critic_in/out: value tables f32[N][D][8] (column 0).  scalars f32[N][4] = {actor_loss, critic_loss,
+ * |g_actor|, |g_critic|}.  outer_product_quirk != 0 reproduces Q16 (a2c.py:60 broadcast).           */
+int toued_a2c_update(const int32_t* obs, const uint8_t* action, const float* reward, const uint8_t* done,
+                     const uint16_t* sorted_tok, const float* actor_in, const float* critic_in,
+                     float* actor_out, float* critic_out, const void* levels, int32_t* step,
+                     float* scalars, int n_agents, int n_workers, int rollout_len, int obs_dim,
+                     float lr_actor, float lr_critic, float max_grad_norm, float gamma, float gae_lambda,
+                     float entropy_coeff, int outer_product_quirk, void* stream);
+
 /* ---- agent (re-)creation (agents/agents.py:31-95, level_sampler.py:273-291) --------------------- */
 
 /* lecun-normal tables from threefry keys: keys u32[N][2], mask u8[N] or NULL (only masked agents are

@@ -55,6 +55,7 @@ SIGNATURES = {
     "toued_wgrad_tc_splits": [],
     "toued_lpg_wgrad_tc": [_P] * 8 + [_I] * 4 + [_P],
     "toued_adam": [_P] * 4 + [_I, _I] + [_F] * 4 + [_P],
+    "toued_a2c_update": [_P] * 12 + [_I] * 4 + [_F] * 6 + [_I, _P],
     "toued_init_tables": [_P] * 3 + [_I] * 3 + [_P],
     "toued_masked_reset": [_P] * 5 + [_I] * 3 + [_P],
     "toued_tc_gemm_test": [_P] * 5,

@@ -1,7 +1,17 @@
-"""A2C antagonist (reference agents/a2c.py:12-125), used by the algorithmic-regret level score."""
+"""A2C antagonist (reference agents/a2c.py:12-125), batched over agents, on csrc/a2c_update.cu.
+
+Used by the algorithmic-regret level score (environments/level_sampler.py:293-329): a fresh A2C agent
+is trained on the level for ``max_lifetime`` updates and its return is compared with the LPG agent's."""
 from __future__ import annotations
 
 from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..util import prng
+from ..util.data import AgentState
 
 
 @dataclass
@@ -12,6 +22,51 @@ class A2CHyperparams:
     entropy_coeff: float
 
 
-def train_a2c_agent(rng, agent_state, rollout_manager, num_train_steps, hypers: A2CHyperparams):
-    """agents/a2c.py:79-125 — CUDA kernels for the A2C update are the next widening step."""
-    raise NotImplementedError("A2C antagonist kernels are not built yet (score_function=alg_regret)")
+def train_a2c_agent(rng, agent_state: AgentState, rollout_manager, num_train_steps: int, hypers: A2CHyperparams,
+                    outer_product_quirk: bool = True, record=None):
+    """agents/a2c.py:79-125, batched: rng uint32[N, 2].  Returns (agent_state, metrics dict of f32[N]).
+    ``record`` (a list) receives the per-update Transition objects (tests only)."""
+    from ..environments.gridworld.gridworld import EnvState
+    from ..util.data import Transition
+    env = rollout_manager.env
+    actor, critic = agent_state.actor_state, agent_state.critic_state
+    N, W = agent_state.env_state.packed.shape
+    L, D, K = rollout_manager.train_rollout_len, env.obs_dim, num_train_steps
+    dev = actor.params.device
+    i32, f32, u8 = torch.int32, torch.float32, torch.uint8
+    a = [actor.params.clone(), torch.empty_like(actor.params)]
+    c = [critic.params.clone(), torch.empty_like(critic.params)]
+    step = actor.step.clone()
+    state = agent_state.env_state.packed.clone()
+    obs = torch.empty((N, L + 1, W), dtype=i32, device=dev)
+    act = torch.empty((N, L, W), dtype=u8, device=dev)
+    rew = torch.empty((N, L, W), dtype=f32, device=dev)
+    don = torch.empty((N, L, W), dtype=u8, device=dev)
+    st = torch.empty((N, L * W), dtype=torch.int16, device=dev)
+    scal = torch.empty((N, 4), dtype=f32, device=dev)
+    msum = torch.zeros((N, 2), dtype=f32, device=dev)
+    levels = agent_state.level.packed
+    rng = np.asarray(rng, np.uint32).reshape(-1, 2)
+    keys = np.empty((K, N, 2), np.uint32)
+    for k in range(K):                                        # a2c.py:95-96
+        ks = prng.split(rng, 2)
+        rng, keys[k] = ks[:, 0, :], ks[:, 1, :]
+    keys_d = torch.from_numpy(keys.view(np.int32)).to(dev, non_blocking=True)
+    p, s = _lib.ptr, _lib.stream_ptr()
+    for k in range(K):
+        i, o = k & 1, (k & 1) ^ 1
+        _lib.call("toued_rollout", p(levels), p(keys_d[k]), p(a[i]), None, p(state), p(obs), p(act), p(rew), p(don),
+                  None, N, W, L, D, env.max_grid_size, env.max_n_objs, 0, s)
+        _lib.call("toued_sort_tokens", p(obs), p(st), N, W, L, s)
+        _lib.call("toued_a2c_update", p(obs), p(act), p(rew), p(don), p(st), p(a[i]), p(c[i]), p(a[o]), p(c[o]),
+                  p(levels), p(step), p(scal), N, W, L, D, float(actor.learning_rate), float(critic.learning_rate),
+                  float(actor.max_grad_norm), float(hypers.gamma), float(hypers.gae_lambda),
+                  float(hypers.entropy_coeff), int(outer_product_quirk), s)
+        msum += scal[:, :2]
+        if record is not None:
+            record.append(Transition(obs.clone(), act.clone(), rew.clone(), don.clone()))
+    f = K & 1
+    out = agent_state.replace(actor_state=actor.replace(params=a[f], step=step),
+                              critic_state=critic.replace(params=c[f], step=step.clone()),
+                              env_obs=obs[:, -1].clone(), env_state=EnvState(state, env.max_n_objs))
+    return out, {"actor_loss": msum[:, 0] / K, "critic_loss": msum[:, 1] / K}
