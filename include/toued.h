@@ -71,14 +71,16 @@ int toued_lpg_prepare(const int32_t* obs, const uint8_t* action, const float* re
                       const uint8_t* done, const float* actor, const float* critic,
                       const float* lpg_params, const int32_t* step, const void* levels, float* x,
                       void* ximg, int n_agents, int n_workers, int rollout_len, int obs_dim,
-                      int lifetime_conditioning, void* stream);
+                      int lifetime_conditioning, int lpg_stride, void* stream);
 
 /* lpg.py:11-30,77-84: reverse GRU with done-reset, relu, heads.  Exact-fp32 SIMT path.
  *   h_out f32[L][R][256]; gates f32[4][L][R][256] (r, z, n, Whn h + bhn) or NULL;
- *   pi_hat f32[L][R]; y_hat f32[L][R][8]                                                          */
+ *   pi_hat f32[L][R]; y_hat f32[L][R][8]
+ * lpg_stride (here and in toued_lpg_prepare): 0 = one shared parameter vector; otherwise agent n uses
+ * lpg_params + n * lpg_stride (per-candidate parameters of the ES path, meta/train.py:167-176).    */
 int toued_gru_forward(const float* x, const uint8_t* done, const float* lpg_params, float* h_out,
                       float* gates, float* pi_hat, float* y_hat, int n_agents, int n_workers,
-                      int rollout_len, int lifetime_conditioning, void* stream);
+                      int rollout_len, int lifetime_conditioning, int lpg_stride, void* stream);
 
 /* lpg_agent.py:60-85,119-120 + optim.py:6-11: closed-form actor/critic gradients, clip-by-global-
  * norm SGD, lifetime mask, step += keep, entropies of the updated nets.
@@ -158,6 +160,17 @@ int toued_a2c_update(const int32_t* obs, const uint8_t* action, const float* rew
                      float* scalars, int n_agents, int n_workers, int rollout_len, int obs_dim,
                      float lr_actor, float lr_critic, float max_grad_norm, float gamma, float gae_lambda,
                      float entropy_coeff, int outer_product_quirk, void* stream);
+
+/* ---- OpenES ask / tell (evosax==0.1.4, meta/train.py:133-227) ----------------------------------- */
+/* candidates f32[popsize][cand_stride] (first P of each row used; cand_stride a multiple of 4 floats so
+ * every candidate is 16-byte aligned) in pair-adjacent order (2i = mean + sigma z_i, 2i+1 = mean - sigma z_i). */
+int toued_es_ask(const uint32_t* key, const float* mean, float sigma, float* candidates, int popsize,
+                 int n_params, int cand_stride, void* stream);
+/* fitness f32[popsize] (higher is better; negated internally like evosax maximize=True); in-place Adam
+ * step on `mean` with state m, v; gen_counter is 0-based.                                            */
+int toued_es_tell(const float* candidates, const float* fitness, float* mean, float* m, float* v,
+                  int popsize, int n_params, int cand_stride, float sigma, float lrate, float beta1,
+                  float beta2, float eps, int gen_counter, float mean_decay, void* stream);
 
 /* ---- agent (re-)creation (agents/agents.py:31-95, level_sampler.py:273-291) --------------------- */
 

@@ -66,7 +66,7 @@ def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond):
         tape.reward[0].copy_(traj.reward); tape.done[0].copy_(traj.done)
         _lib.call("toued_lpg_prepare", p(tape.obs[0]), p(tape.action[0]), p(tape.reward[0]), p(tape.done[0]),
                   p(ag.actor_state.params), p(ag.critic_state.params), p(lpg), p(ag.actor_state.step),
-                  p(ag.level.packed), p(tape.x[0]), None, n, c.w, c.L, c.D, int(cond), s)
+                  p(ag.level.packed), p(tape.x[0]), None, n, c.w, c.L, c.D, int(cond), 0, s)
         if prec == "tc":
             _lib.call("toued_pack_wh_forward", p(lpg), p(tape.wh_img), s)
             _lib.call("toued_gru_forward_tc", p(tape.x[0]), p(tape.done[0]), p(lpg), p(tape.wh_img), p(tape.h16[0]),
@@ -77,7 +77,7 @@ def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond):
             out["hpimg"] = tape.hpimg[0].clone()
         else:
             _lib.call("toued_gru_forward", p(tape.x[0]), p(tape.done[0]), p(lpg), p(tape.h[0]), p(tape.gates[0]),
-                      p(tape.pi_hat[0]), p(tape.y_hat[0]), n, c.w, c.L, int(cond), s)
+                      p(tape.pi_hat[0]), p(tape.y_hat[0]), n, c.w, c.L, int(cond), 0, s)
             r_, z_, n_, hn_ = tape.gates[0]
             h_ = tape.h[0]
             nd = (1 - tape.done[0].float()).permute(1, 0, 2).reshape(c.L, n * c.w, 1)     # [L][R][1]

@@ -38,8 +38,8 @@ SIGNATURES = {
     "toued_env_step": [_P] * 7 + [_I] * 4 + [_P],
     "toued_env_reset": [_P] * 3 + [_I] * 3 + [_P],
     "toued_sort_tokens": [_P] * 2 + [_I] * 3 + [_P],
-    "toued_lpg_prepare": [_P] * 11 + [_I] * 5 + [_P],
-    "toued_gru_forward": [_P] * 7 + [_I] * 4 + [_P],
+    "toued_lpg_prepare": [_P] * 11 + [_I] * 6 + [_P],
+    "toued_gru_forward": [_P] * 7 + [_I] * 5 + [_P],
     "toued_agent_update": [_P] * 12 + [_I] * 4 + [_F] * 4 + [_P],
     "toued_meta_loss": [_P] * 10 + [_I] * 5 + [_F] * 3 + [_I, _P],
     "toued_agent_backward": [_P] * 14 + [_I] * 4 + [_F] * 9 + [_P],
@@ -55,6 +55,8 @@ SIGNATURES = {
     "toued_wgrad_tc_splits": [],
     "toued_lpg_wgrad_tc": [_P] * 8 + [_I] * 4 + [_P],
     "toued_adam": [_P] * 4 + [_I, _I] + [_F] * 4 + [_P],
+    "toued_es_ask": [_P, _P, _F, _P, _I, _I, _I, _P],
+    "toued_es_tell": [_P] * 5 + [_I, _I, _I] + [_F] * 5 + [_I, _F, _P],
     "toued_a2c_update": [_P] * 12 + [_I] * 4 + [_F] * 6 + [_I, _P],
     "toued_init_tables": [_P] * 3 + [_I] * 3 + [_P],
     "toued_masked_reset": [_P] * 5 + [_I] * 3 + [_P],

@@ -74,16 +74,20 @@ lpg_prepare_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ 
                    const float* __restrict__ actor, const float* __restrict__ critic,
                    const float* __restrict__ lpg, const int32_t* __restrict__ step,
                    const LevelRec* __restrict__ levels, float* __restrict__ x, unsigned char* __restrict__ ximg,
-                   int n_agents, int W, int L, int D, int cond, int emb_off) {
-    __shared__ float sp[LPG_Y * LPG_E + LPG_E + LPG_E + 1];
-    for (int i = threadIdx.x; i < LPG_Y * LPG_E + 2 * LPG_E + 1; i += blockDim.x) sp[i] = lpg[emb_off + i];
-    __syncthreads();
+                   int n_agents, int W, int L, int D, int cond, int emb_off, int lpg_stride) {
+    __shared__ float sp_s[LPG_Y * LPG_E + LPG_E + LPG_E + 1];
+    if (lpg_stride == 0) {
+        for (int i = threadIdx.x; i < LPG_Y * LPG_E + 2 * LPG_E + 1; i += blockDim.x) sp_s[i] = lpg[emb_off + i];
+        __syncthreads();
+    }
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t total = (size_t)n_agents * L * W;
     if (g >= total) return;
     const int w = (int)(g % W);
     const int t = (int)((g / W) % L);
     const int n = (int)(g / ((size_t)W * L));
+    // per-agent LPG parameters (ES candidates): read the embedding MLP straight from global / L2
+    const float* sp = lpg_stride ? lpg + (size_t)n * lpg_stride + emb_off : sp_s;
     const int32_t ob = obs[((size_t)n * (L + 1) + t) * W + w];
     const int32_t ob1 = obs[((size_t)n * (L + 1) + t + 1) * W + w];
     const float* at = actor + (size_t)n * D * 8;
@@ -123,13 +127,13 @@ extern "C" int toued_lpg_prepare(const int32_t* obs, const uint8_t* action, cons
                                  const uint8_t* done, const float* actor, const float* critic,
                                  const float* lpg_params, const int32_t* step, const void* levels,
                                  float* x, void* ximg, int n_agents, int n_workers, int rollout_len, int obs_dim,
-                                 int lifetime_conditioning, void* stream) {
+                                 int lifetime_conditioning, int lpg_stride, void* stream) {
     const size_t total = (size_t)n_agents * rollout_len * n_workers;
     TOUED_CHECK(total > 0, "toued_lpg_prepare: empty problem");
     lpg_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         obs, action, reward, done, actor, critic, lpg_params, step, (const LevelRec*)levels, x, (unsigned char*)ximg,
         n_agents, n_workers, rollout_len, obs_dim, lifetime_conditioning,
-        lpg_offsets(lifetime_conditioning ? 7 : 5).e_w0);
+        lpg_offsets(lifetime_conditioning ? 7 : 5).e_w0, lpg_stride);
     TOUED_LAUNCH_CHECK();
     return 0;
 }
@@ -150,8 +154,10 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 template <int X>
 __global__ void __launch_bounds__(256, 1)
 gru_forward_kernel(const float* __restrict__ x, const uint8_t* __restrict__ done,
-                   const float* __restrict__ lpg, float* __restrict__ h_out, float* __restrict__ gates,
-                   float* __restrict__ pi_hat, float* __restrict__ y_hat, int R, int L, int W) {
+                   const float* __restrict__ lpg_base, float* __restrict__ h_out, float* __restrict__ gates,
+                   float* __restrict__ pi_hat, float* __restrict__ y_hat, int R, int L, int W, int lpg_stride) {
+    // per-agent LPG parameters (ES candidates): the CTA's 64 rows belong to one agent (W % 64 == 0)
+    const float* lpg = lpg_base + (size_t)((blockIdx.x * 64) / W) * lpg_stride;
     extern __shared__ __align__(16) float sm[];
     float* hA = sm;                                  // [64][GF_HS] h' (masked carry)
     float* hB = hA + GF_TM * GF_HS;                  // [64][GF_HS] new h
@@ -335,19 +341,20 @@ static size_t gru_fwd_smem(int X) {
 
 extern "C" int toued_gru_forward(const float* x, const uint8_t* done, const float* lpg_params, float* h_out,
                                  float* gates, float* pi_hat, float* y_hat, int n_agents, int n_workers,
-                                 int rollout_len, int lifetime_conditioning, void* stream) {
+                                 int rollout_len, int lifetime_conditioning, int lpg_stride, void* stream) {
     const int R = n_agents * n_workers;
     TOUED_CHECK(R > 0 && rollout_len > 0, "toued_gru_forward: empty problem");
+    TOUED_CHECK(lpg_stride == 0 || n_workers % 64 == 0, "toued_gru_forward: per-agent parameters need n_workers %% 64 == 0");
     const int blocks = (R + GF_TM - 1) / GF_TM;
     cudaStream_t st = (cudaStream_t)stream;
     if (lifetime_conditioning) {
         const size_t smem = gru_fwd_smem(7);
         TOUED_CUDA(cudaFuncSetAttribute(gru_forward_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gru_forward_kernel<7><<<blocks, 256, smem, st>>>(x, done, lpg_params, h_out, gates, pi_hat, y_hat, R, rollout_len, n_workers);
+        gru_forward_kernel<7><<<blocks, 256, smem, st>>>(x, done, lpg_params, h_out, gates, pi_hat, y_hat, R, rollout_len, n_workers, lpg_stride);
     } else {
         const size_t smem = gru_fwd_smem(5);
         TOUED_CUDA(cudaFuncSetAttribute(gru_forward_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gru_forward_kernel<5><<<blocks, 256, smem, st>>>(x, done, lpg_params, h_out, gates, pi_hat, y_hat, R, rollout_len, n_workers);
+        gru_forward_kernel<5><<<blocks, 256, smem, st>>>(x, done, lpg_params, h_out, gates, pi_hat, y_hat, R, rollout_len, n_workers, lpg_stride);
     }
     TOUED_LAUNCH_CHECK();
     return 0;
