@@ -172,6 +172,13 @@ int toued_es_tell(const float* candidates, const float* fitness, float* mean, fl
                   int popsize, int n_params, int cand_stride, float sigma, float lrate, float beta1,
                   float beta2, float eps, int gen_counter, float mean_decay, void* stream);
 
+/* ---- double-oracle Nash solver (environments/nash_sampler.py:24-58, util/projection.py:9-38) ------ */
+/* game f32[n][n] (row player x minimises x^T G y), supports = first x_nz / y_nz coordinates, n <= 1024.
+ * Averaged iterates of num_iters projected-gradient steps (reference: 10,000 steps, lr 0.01).        */
+int toued_get_nash(const float* game, const float* x0, const float* y0, float* x_out, float* y_out,
+                   int n, int x_nz, int y_nz, int num_iters, float lr, void* stream);
+int toued_projection_simplex(float* v, int n, int max_nz, void* stream);
+
 /* ---- agent (re-)creation (agents/agents.py:31-95, level_sampler.py:273-291) --------------------- */
 
 /* lecun-normal tables from threefry keys: keys u32[N][2], mask u8[N] or NULL (only masked agents are

@@ -55,6 +55,8 @@ SIGNATURES = {
     "toued_wgrad_tc_splits": [],
     "toued_lpg_wgrad_tc": [_P] * 8 + [_I] * 4 + [_P],
     "toued_adam": [_P] * 4 + [_I, _I] + [_F] * 4 + [_P],
+    "toued_get_nash": [_P] * 5 + [_I] * 4 + [_F, _P],
+    "toued_projection_simplex": [_P, _I, _I, _P],
     "toued_es_ask": [_P, _P, _F, _P, _I, _I, _I, _P],
     "toued_es_tell": [_P] * 5 + [_I, _I, _I] + [_F] * 5 + [_I, _F, _P],
     "toued_a2c_update": [_P] * 12 + [_I] * 4 + [_F] * 6 + [_I, _P],
