@@ -153,7 +153,8 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_global = AGENTS_PER_GPU * world
-    args = parse_args(["--env_mode", ENV_MODE, "--num_agents", str(n_global), "--num_mini_batches", "1"])
+    mini_batches = int(os.environ.get("TOUED_BENCH_MINI_BATCHES", "2"))
+    args = parse_args(["--env_mode", ENV_MODE, "--num_agents", str(n_global), "--num_mini_batches", str(mini_batches)])
     rng = prng.PRNGKey(args.seed)
     rng, lpg_rng, buffer_rng = prng.split(rng, 3)
     train_state = create_lpg_train_state(lpg_rng, args)
@@ -272,7 +273,8 @@ def run_ours(a):
         "dtype": "f16/bf16 operands, f32 accumulate (GRU); f32 elsewhere" if precision == "tc" else "f32", "data": "synthetic",
         "config": {"workload": f"LPG meta-gradient step (train.py loop body), env_mode={ENV_MODE}, "
                                f"{AGENTS_PER_GPU} agents/GPU x {W} workers x {L} steps x K={K} updates, "
-                               "num_mini_batches=1 (reference README uses 16 as a memory device; results identical)",
+                               f"num_mini_batches={mini_batches} run concurrently on CUDA streams (the reference README uses 16 "
+                               "sequential mini-batches as a memory device; results identical)",
                    "gru_precision": precision, "agents_per_gpu": AGENTS_PER_GPU, "global_agents": n_global, "env_steps_per_meta_step": total_env_steps,
                    "l2_policy": "working set per step (>15 GB of activations) exceeds L2; no explicit flush"},
         "meta_steps_per_s": 1e3 / ms_per_step,

@@ -5,3 +5,7 @@ import os
 #   "tc"   tcgen05 tensor cores, fp16 operands / fp32 accumulation in TMEM (production path)
 #   "fp32" exact-fp32 SIMT kernels (numerical baseline)
 GRU_PRECISION = os.environ.get("TOUED_GRU_PRECISION", "tc")
+
+# Number of CUDA streams on which independent mini-batches of agents run concurrently inside one meta-step
+# (only used when num_mini_batches > 1; results are independent of it).
+NUM_STREAMS = int(os.environ.get("TOUED_NUM_STREAMS", "4"))

@@ -70,16 +70,26 @@ class MetaGradWorkspace:
 
 
 _WS_CACHE = {}
+_STREAMS = {}
 
 
-def _workspace(n, w, L, D, K, P, device) -> MetaGradWorkspace:
+def _workspace(n, w, L, D, K, P, device, slot=0) -> MetaGradWorkspace:
     import to_ued_b200
     key = (n, w, L, D, K, P, str(device), to_ued_b200.GRU_PRECISION)
-    ws = _WS_CACHE.get(key)
-    if ws is None:
+    if _WS_CACHE and next(iter(_WS_CACHE))[:-1] != key:
         _WS_CACHE.clear()
-        ws = _WS_CACHE[key] = MetaGradWorkspace(n, w, L, D, K, P, device)
+    ws = _WS_CACHE.get(key + (slot,))
+    if ws is None:
+        ws = _WS_CACHE[key + (slot,)] = MetaGradWorkspace(n, w, L, D, K, P, device)
     return ws
+
+
+def _side_streams(device, n):
+    key = str(device)
+    lst = _STREAMS.setdefault(key, [])
+    while len(lst) < n:
+        lst.append(torch.cuda.Stream(device=device))
+    return lst[:n]
 
 
 def _world():
@@ -93,7 +103,7 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                              rollout_manager, num_mini_batches: int, gamma: float, gae_lambda: float,
                              lpg_hypers: LpgHyperparams, *, outer_product_quirk: bool = True,
                              global_agent_offset: int = 0, global_num_agents: Optional[int] = None,
-                             eval_workers: int = 4, return_grad: bool = False):
+                             eval_workers: int = 4, return_grad: bool = False, num_streams: Optional[int] = None):
     """Update a batch of agents with LPG, then update LPG with the regularised final agent loss
     (meta/train.py:14-130).  rng: the step key (uint32[2]).  Returns
     (lpg_train_state, agent_states, value_critic_states, metrics)."""
@@ -121,91 +131,117 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     if N % num_mini_batches != 0:
         raise ValueError(f"local agents ({N}) must be divisible by num_mini_batches ({num_mini_batches})")
     nb = N // num_mini_batches
-    ws = _workspace(nb, W, L, D, K, P, dev)
-    tape = ws.tape
+    # Mini-batches are independent chains of kernels: run up to `num_streams` of them concurrently on side
+    # streams (each with its own workspace) so that one chain's latency-bound kernels and wave tails overlap
+    # with another chain's GEMMs.  Results are identical to the sequential order (partials are per workspace).
+    import to_ued_b200
+    if num_streams is None:
+        num_streams = to_ued_b200.NUM_STREAMS
+    S = max(1, min(int(num_streams), num_mini_batches))
+    wss = [_workspace(nb, W, L, D, K, P, dev, slot=i) for i in range(S)]
+    main = torch.cuda.current_stream()
+    streams = [main] if S == 1 else _side_streams(dev, S)
+    tc = wss[0].tape.precision == "tc"
     gscale = 1.0 / n_global
     bK = [c / K for c in (lpg_hypers.policy_entropy_coeff, lpg_hypers.target_entropy_coeff,
                           lpg_hypers.policy_l2_coeff, lpg_hypers.target_l2_coeff)]
-    tc = tape.precision == "tc"
-    if tc:
-        _lib.call("toued_pack_wh_backward", p(lpg), p(ws.whb_img), s)
-    else:
-        _lib.call("toued_transpose_wh", p(lpg), p(ws.whT), s)
-
     new_actor = torch.empty_like(actor.params)
     new_critic = torch.empty_like(critic.params)
     new_step = torch.empty_like(actor.step)
     new_state = torch.empty_like(agent_states.env_state.packed)
     new_obs = torch.empty_like(agent_states.env_obs)
-    msum = torch.zeros(8, dtype=torch.float32, device=dev)
-    levels_all = agent_states.level.packed
+    msums = [torch.zeros(8, dtype=torch.float32, device=dev) for _ in range(S)]
     returns = torch.empty(N, dtype=torch.float32, device=dev)
+    ready = torch.cuda.Event()
+    ready.record(main)
 
     for mb in range(num_mini_batches):
-        sl = slice(mb * nb, (mb + 1) * nb)
-        sub = AgentState(actor.replace(params=actor.params[sl], step=actor.step[sl]),
-                         critic.replace(params=critic.params[sl], step=critic.step[sl]),
-                         _sub_level(agent_states.level, sl), agent_states.env_obs[sl],
-                         EnvState(agent_states.env_state.packed[sl], env.max_n_objs))
-        levels = sub.level.packed
-        # ---- K agent updates (forward, taped) ----
-        sub2, _, am = train_lpg_agent(r_train[sl], lpg_train_state, sub, rollout_manager, K,
-                                      lpg_hypers.agent_target_coeff, tape=tape)
-        # ---- rollout the updated agent (meta/train.py:46-58) ----
-        state = sub2.env_state.packed
-        keys_e = torch.from_numpy(np.ascontiguousarray(r_eval[sl]).view(np.int32)).to(dev, non_blocking=True)
-        _lib.call("toued_rollout", p(levels), p(keys_e), p(tape.actor[K]), None, p(state), p(tape.obs[K]),
-                  p(tape.action[K]), p(tape.reward[K]), p(tape.done[K]), None, nb, W, L, D,
-                  env.max_grid_size, env.max_n_objs, 0, s)
-        _lib.call("toued_sort_tokens", p(tape.obs[K]), p(tape.sorted_tok[K]), nb, W, L, s)
-        # ---- value "update" (Q2) + advantage + LPG loss + lam_K (meta/train.py:60-100) ----
-        vparams = value_critic_states.params[sl]
-        _lib.call("toued_meta_loss", p(tape.obs[K]), p(tape.action[K]), p(tape.reward[K]), p(tape.done[K]),
-                  p(tape.sorted_tok[K]), p(vparams), p(tape.actor[K]), p(ws.lam), p(ws.mu), p(ws.loss_scal),
-                  nb, W, L, D, vparams.shape[-1], float(gamma), float(gae_lambda), float(gscale),
-                  int(outer_product_quirk), s)
-        # ---- reverse pass ----
-        for k in reversed(range(K)):
-            _lib.call("toued_agent_backward", p(tape.obs[k]), p(tape.action[k]), p(tape.sorted_tok[k]),
-                      p(tape.pi_hat[k]), p(tape.y_hat[k]), p(tape.actor[k]), p(tape.critic[k]),
-                      p(tape.actor[k + 1]), p(tape.critic[k + 1]), p(tape.scalars[k]), p(ws.lam), p(ws.mu),
-                      p(ws.d_pi_hat), p(ws.d_y_hat), nb, W, L, D, float(actor.learning_rate),
-                      float(critic.learning_rate), float(actor.max_grad_norm),
-                      float(lpg_hypers.agent_target_coeff), *[float(b) for b in bK], float(gscale), s)
-            first = (mb == 0 and k == K - 1)
-            if tc:
-                _lib.call("toued_gru_backward_tc", p(tape.done[k]), p(lpg), p(ws.whb_img), p(tape.h16[k]),
-                          p(tape.fac[k]), p(tape.y_hat[k]), p(ws.d_pi_hat), p(ws.d_y_hat), p(ws.dgimg), p(ws.dl),
-                          p(ws.dx), nb, W, L, cond, s)
-                _lib.call("toued_lpg_wgrad_tc", p(tape.hpimg[k]), p(ws.dgimg), p(tape.ximg[k]), p(tape.h16[k]),
-                          p(ws.d_pi_hat), p(ws.dl), p(ws.partials), p(ws.partials[ws.off_small:]),
-                          nb, W, L, 0 if first else 1, s)
-                _lib.call("toued_lpg_wgrad_embed", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg),
-                          p(ws.dx), p(ws.partials), nb, W, L, D, cond, 0 if first else 1, s)
-            else:
-                _lib.call("toued_gru_backward", p(tape.done[k]), p(lpg), p(ws.whT), p(tape.h[k]), p(tape.gates[k]),
-                          p(tape.y_hat[k]), p(ws.d_pi_hat), p(ws.d_y_hat), p(ws.dl), p(ws.dx), nb, W, L, cond, s)
-                _lib.call("toued_lpg_wgrad", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg), p(tape.x[k]),
-                          p(tape.h[k]), p(tape.gates[k]), p(ws.d_pi_hat), p(ws.dl), p(ws.dx), p(ws.partials),
-                          nb, W, L, D, cond, 0 if first else 1, s)
-        # ---- metrics (sums over agents; divided by n_global after the all-reduce) ----
-        lpg_loss, value_loss = ws.loss_scal[:, 0], ws.loss_scal[:, 1]
-        reg = (lpg_loss - lpg_hypers.policy_entropy_coeff * am.policy_entropy + lpg_hypers.policy_l2_coeff * am.policy_l2
-               - lpg_hypers.target_entropy_coeff * am.critic_entropy + lpg_hypers.target_l2_coeff * am.critic_l2)
-        msum[:7] += torch.stack([lpg_loss.sum(), reg.sum(), value_loss.sum(), am.policy_l2.sum(),
-                                 am.policy_entropy.sum(), am.critic_loss.sum(), am.critic_l2.sum()])
-        msum[7] += am.critic_entropy.sum()
-        new_actor[sl] = sub2.actor_state.params
-        new_critic[sl] = sub2.critic_state.params
-        new_step[sl] = sub2.actor_state.step
-        new_state[sl] = state
-        new_obs[sl] = tape.obs[K][:, -1]
-        # ---- evaluate agent return: 4 workers, metric only (meta/train.py:109-117, Q11) ----
-        returns[sl] = eval_agent(r_evalagent[sl], rollout_manager, levels, tape.actor[K], eval_workers)
+        slot = mb % S
+        ws, tape, msum = wss[slot], wss[slot].tape, msums[slot]
+        with torch.cuda.stream(streams[slot]):
+            if S > 1 and mb < S:
+                streams[slot].wait_event(ready)
+            s = _lib.stream_ptr()
+            if mb < S:
+                if tc:
+                    _lib.call("toued_pack_wh_backward", p(lpg), p(ws.whb_img), s)
+                else:
+                    _lib.call("toued_transpose_wh", p(lpg), p(ws.whT), s)
+            sl = slice(mb * nb, (mb + 1) * nb)
+            sub = AgentState(actor.replace(params=actor.params[sl], step=actor.step[sl]),
+                             critic.replace(params=critic.params[sl], step=critic.step[sl]),
+                             _sub_level(agent_states.level, sl), agent_states.env_obs[sl],
+                             EnvState(agent_states.env_state.packed[sl], env.max_n_objs))
+            levels = sub.level.packed
+            # ---- K agent updates (forward, taped) ----
+            sub2, _, am = train_lpg_agent(r_train[sl], lpg_train_state, sub, rollout_manager, K,
+                                          lpg_hypers.agent_target_coeff, tape=tape)
+            # ---- rollout the updated agent (meta/train.py:46-58) ----
+            state = sub2.env_state.packed
+            keys_e = torch.from_numpy(np.ascontiguousarray(r_eval[sl]).view(np.int32)).to(dev, non_blocking=True)
+            _lib.call("toued_rollout", p(levels), p(keys_e), p(tape.actor[K]), None, p(state), p(tape.obs[K]),
+                      p(tape.action[K]), p(tape.reward[K]), p(tape.done[K]), None, nb, W, L, D,
+                      env.max_grid_size, env.max_n_objs, 0, s)
+            _lib.call("toued_sort_tokens", p(tape.obs[K]), p(tape.sorted_tok[K]), nb, W, L, s)
+            # ---- value "update" (Q2) + advantage + LPG loss + lam_K (meta/train.py:60-100) ----
+            vparams = value_critic_states.params[sl]
+            _lib.call("toued_meta_loss", p(tape.obs[K]), p(tape.action[K]), p(tape.reward[K]), p(tape.done[K]),
+                      p(tape.sorted_tok[K]), p(vparams), p(tape.actor[K]), p(ws.lam), p(ws.mu), p(ws.loss_scal),
+                      nb, W, L, D, vparams.shape[-1], float(gamma), float(gae_lambda), float(gscale),
+                      int(outer_product_quirk), s)
+            # ---- reverse pass ----
+            for k in reversed(range(K)):
+                _lib.call("toued_agent_backward", p(tape.obs[k]), p(tape.action[k]), p(tape.sorted_tok[k]),
+                          p(tape.pi_hat[k]), p(tape.y_hat[k]), p(tape.actor[k]), p(tape.critic[k]),
+                          p(tape.actor[k + 1]), p(tape.critic[k + 1]), p(tape.scalars[k]), p(ws.lam), p(ws.mu),
+                          p(ws.d_pi_hat), p(ws.d_y_hat), nb, W, L, D, float(actor.learning_rate),
+                          float(critic.learning_rate), float(actor.max_grad_norm),
+                          float(lpg_hypers.agent_target_coeff), *[float(b) for b in bK], float(gscale), s)
+                first = (mb < S and k == K - 1)                 # first use of this workspace's partial buffers
+                if tc:
+                    _lib.call("toued_gru_backward_tc", p(tape.done[k]), p(lpg), p(ws.whb_img), p(tape.h16[k]),
+                              p(tape.fac[k]), p(tape.y_hat[k]), p(ws.d_pi_hat), p(ws.d_y_hat), p(ws.dgimg), p(ws.dl),
+                              p(ws.dx), nb, W, L, cond, s)
+                    _lib.call("toued_lpg_wgrad_tc", p(tape.hpimg[k]), p(ws.dgimg), p(tape.ximg[k]), p(tape.h16[k]),
+                              p(ws.d_pi_hat), p(ws.dl), p(ws.partials), p(ws.partials[ws.off_small:]),
+                              nb, W, L, 0 if first else 1, s)
+                    _lib.call("toued_lpg_wgrad_embed", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg),
+                              p(ws.dx), p(ws.partials), nb, W, L, D, cond, 0 if first else 1, s)
+                else:
+                    _lib.call("toued_gru_backward", p(tape.done[k]), p(lpg), p(ws.whT), p(tape.h[k]), p(tape.gates[k]),
+                              p(tape.y_hat[k]), p(ws.d_pi_hat), p(ws.d_y_hat), p(ws.dl), p(ws.dx), nb, W, L, cond, s)
+                    _lib.call("toued_lpg_wgrad", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg), p(tape.x[k]),
+                              p(tape.h[k]), p(tape.gates[k]), p(ws.d_pi_hat), p(ws.dl), p(ws.dx), p(ws.partials),
+                              nb, W, L, D, cond, 0 if first else 1, s)
+            # ---- metrics (sums over agents; divided by n_global after the all-reduce) ----
+            lpg_loss, value_loss = ws.loss_scal[:, 0], ws.loss_scal[:, 1]
+            reg = (lpg_loss - lpg_hypers.policy_entropy_coeff * am.policy_entropy + lpg_hypers.policy_l2_coeff * am.policy_l2
+                   - lpg_hypers.target_entropy_coeff * am.critic_entropy + lpg_hypers.target_l2_coeff * am.critic_l2)
+            msum[:7] += torch.stack([lpg_loss.sum(), reg.sum(), value_loss.sum(), am.policy_l2.sum(),
+                                     am.policy_entropy.sum(), am.critic_loss.sum(), am.critic_l2.sum()])
+            msum[7] += am.critic_entropy.sum()
+            new_actor[sl] = sub2.actor_state.params
+            new_critic[sl] = sub2.critic_state.params
+            new_step[sl] = sub2.actor_state.step
+            new_state[sl] = state
+            new_obs[sl] = tape.obs[K][:, -1]
+            # ---- evaluate agent return: 4 workers, metric only (meta/train.py:109-117, Q11) ----
+            returns[sl] = eval_agent(r_evalagent[sl], rollout_manager, levels, tape.actor[K], eval_workers)
+    if S > 1:
+        for st in streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+    s = _lib.stream_ptr()
+    msum = msums[0] if S == 1 else torch.stack(msums).sum(0)
 
     grad = torch.empty(P, dtype=torch.float32, device=dev)
-    _lib.call("toued_reduce_partials", p(ws.partials), p(grad), cond,
-              _lib.lib().toued_wgrad_tc_splits() if tc else 32, s)
+    n_wh = _lib.lib().toued_wgrad_tc_splits() if tc else 32
+    _lib.call("toued_reduce_partials", p(wss[0].partials), p(grad), cond, n_wh, s)
+    for ws in wss[1:min(S, num_mini_batches)]:
+        g2 = torch.empty_like(grad)
+        _lib.call("toued_reduce_partials", p(ws.partials), p(g2), cond, n_wh, s)
+        grad += g2
     mvec = torch.cat([msum, returns.sum().view(1)])
     if dist is not None:
         dist.all_reduce(grad)                     # sum of per-rank (1/n_global)-scaled sums = mean
