@@ -158,23 +158,48 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
         const size_t gs = (size_t)L * R32 * 32 * LPG_H;
         const size_t Rp = ((size_t)R + 63) & ~(size_t)63;
         uint32_t ait = 0;
+        // ---- software pipeline: the factor loads of the next 8-unit chunk and the head cotangents of the
+        //      next timestep are issued one iteration ahead (across unit-block / timestep boundaries) ----
+        struct FacLoads { uint4 fr, fz, fhn, fan, zz, hv; };
+        auto issue_fac = [&](int t_, int ub_, int c8_) {
+            FacLoads l;
+            const size_t base = rb32_index((size_t)t_, R32, rsafe, ub_ * 64 + hf * 32 + c8_ * 8);
+            l.fr = *reinterpret_cast<const uint4*>(fac + base);
+            l.fz = *reinterpret_cast<const uint4*>(fac + gs + base);
+            l.fhn = *reinterpret_cast<const uint4*>(fac + 2 * gs + base);
+            l.fan = *reinterpret_cast<const uint4*>(fac + 3 * gs + base);
+            l.zz = *reinterpret_cast<const uint4*>(fac + 4 * gs + base);
+            l.hv = *reinterpret_cast<const uint4*>(h16 + base);
+            return l;
+        };
+        struct RowLoads { float4 y0, y1, d0, d1; float dpi; uint8_t dn; };
+        auto issue_row = [&](int t_) {
+            RowLoads r;
+            const size_t tok_ = (size_t)t_ * R + rsafe;
+            const float4* q0 = reinterpret_cast<const float4*>(y_hat + tok_ * 8);
+            const float4* q1 = reinterpret_cast<const float4*>(d_y_hat + tok_ * 8);
+            r.y0 = q0[0]; r.y1 = q0[1]; r.d0 = q1[0]; r.d1 = q1[1];
+            r.dpi = d_pi_hat[tok_];
+            r.dn = t_ > 0 ? done[((size_t)n_ag * L + (t_ - 1)) * W + w_ag] : (uint8_t)1;
+            return r;
+        };
+        FacLoads nxt = issue_fac(0, 0, 0);
+        RowLoads rnx = issue_row(0);
         for (int t = 0; t < L; ++t) {
             const size_t tok = (size_t)t * R + rsafe;
             // head cotangents of this row (softmax backward of y_hat), lpg.py:83-84
             float dl[8], dpi;
+            const RowLoads rc = rnx;
+            if (t + 1 < L) rnx = issue_row(t + 1);
             {
-                float yh[8], dy[8];
-                const float4* q0 = reinterpret_cast<const float4*>(y_hat + tok * 8);
-                const float4* q1 = reinterpret_cast<const float4*>(d_y_hat + tok * 8);
-                const float4 a0 = q0[0], a1 = q0[1], b0 = q1[0], b1 = q1[1];
-                yh[0] = a0.x; yh[1] = a0.y; yh[2] = a0.z; yh[3] = a0.w; yh[4] = a1.x; yh[5] = a1.y; yh[6] = a1.z; yh[7] = a1.w;
-                dy[0] = b0.x; dy[1] = b0.y; dy[2] = b0.z; dy[3] = b0.w; dy[4] = b1.x; dy[5] = b1.y; dy[6] = b1.z; dy[7] = b1.w;
+                const float yh[8] = {rc.y0.x, rc.y0.y, rc.y0.z, rc.y0.w, rc.y1.x, rc.y1.y, rc.y1.z, rc.y1.w};
+                const float dy[8] = {rc.d0.x, rc.d0.y, rc.d0.z, rc.d0.w, rc.d1.x, rc.d1.y, rc.d1.z, rc.d1.w};
                 float s = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) s = fmaf(yh[i], dy[i], s);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) dl[i] = rv ? yh[i] * (dy[i] - s) : 0.0f;
-                dpi = rv ? d_pi_hat[tok] : 0.0f;
+                dpi = rv ? rc.dpi : 0.0f;
                 if (hf == 0 && rv) {
                     float4* qo = reinterpret_cast<float4*>(dl_out + tok * 8);
                     qo[0] = make_float4(dl[0], dl[1], dl[2], dl[3]);
@@ -182,32 +207,31 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                 }
             }
             // carry mask: the cell at step t-1 consumed (1 - done_{t-1}) * h_t
-            const float nd = (t > 0 && rv && !done[((size_t)n_ag * L + (t - 1)) * W + w_ag]) ? 1.0f : 0.0f;
+            const float nd = (t > 0 && rv && !rc.dn) ? 1.0f : 0.0f;
             if (t > 0) { mbar_wait(&q_full, (t - 1) & 1); tc_fence_after(); }
             const uint32_t p_addr = tmem_base + ((t - 1) & 1) * 256 + ((uint32_t)(q * 32) << 16);
             float dx3 = 0.f, dx4 = 0.f;
             for (int ub = 0; ub < 4; ++ub) {
                 const int ubase = ub * 64 + hf * 32;                 // first of this thread's 32 units
-                uint4 outA[5][4];
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {
                     const int u0 = ubase + c8 * 8;
                     float carry[8];
-                    if (t > 0) {
-                        tmem_ld8(p_addr + u0, carry);
-                        tmem_ld_wait();
-                    } else {
+                    if (t > 0) tmem_ld8(p_addr + u0, carry);
+                    const FacLoads cur = nxt;
+                    {   // prefetch the next chunk (next c8, else next unit block, else next timestep)
+                        int t2 = t, ub2 = ub, c2 = c8 + 1;
+                        if (c2 == 4) { c2 = 0; ++ub2; if (ub2 == 4) { ub2 = 0; ++t2; } }
+                        if (t2 < L) nxt = issue_fac(t2, ub2, c2);
+                    }
+                    if (t > 0) tmem_ld_wait();
+                    else {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) carry[e] = 0.f;
                     }
                     float fr[8], fz[8], fhn[8], fan[8], zz[8], hv[8];
-                    const size_t base = rb32_index((size_t)t, R32, rsafe, u0);
-                    unpack8h(*reinterpret_cast<const uint4*>(fac + base), fr);
-                    unpack8h(*reinterpret_cast<const uint4*>(fac + gs + base), fz);
-                    unpack8h(*reinterpret_cast<const uint4*>(fac + 2 * gs + base), fhn);
-                    unpack8h(*reinterpret_cast<const uint4*>(fac + 3 * gs + base), fan);
-                    unpack8h(*reinterpret_cast<const uint4*>(fac + 4 * gs + base), zz);
-                    unpack8h(*reinterpret_cast<const uint4*>(h16 + base), hv);
+                    unpack8h(cur.fr, fr); unpack8h(cur.fz, fz); unpack8h(cur.fhn, fhn);
+                    unpack8h(cur.fan, fan); unpack8h(cur.zz, zz); unpack8h(cur.hv, hv);
                     float gr[8], gz[8], ghn[8], gan[8], czh[8], czl[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
@@ -231,25 +255,28 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                             dx4 = fmaf(gr[e], w0.w, fmaf(gz[e], w1.x, fmaf(gan[e], w1.y, dx4)));
                         }
                     }
-                    outA[0][c8] = pack8bf(gr); outA[1][c8] = pack8bf(gz); outA[2][c8] = pack8bf(ghn);
-                    outA[3][c8] = pack8bf(czh); outA[4][c8] = pack8bf(czl);
+                    const uint4 o_r = pack8bf(gr), o_z = pack8bf(gz), o_hn = pack8bf(ghn);
                     if (rv) {      // token tile image for the weight-gradient kernels: 16 column groups
                         const size_t itok = (size_t)t * Rp + row;
                         const int cin = hf * 32 + c8 * 8;
-                        *reinterpret_cast<uint4*>(dgimg + tile_img_offset(itok, 16, (0 * 4 + ub) * 64 + cin)) = outA[0][c8];
-                        *reinterpret_cast<uint4*>(dgimg + tile_img_offset(itok, 16, (1 * 4 + ub) * 64 + cin)) = outA[1][c8];
-                        *reinterpret_cast<uint4*>(dgimg + tile_img_offset(itok, 16, (2 * 4 + ub) * 64 + cin)) = outA[2][c8];
+                        *reinterpret_cast<uint4*>(dgimg + tile_img_offset(itok, 16, (0 * 4 + ub) * 64 + cin)) = o_r;
+                        *reinterpret_cast<uint4*>(dgimg + tile_img_offset(itok, 16, (1 * 4 + ub) * 64 + cin)) = o_z;
+                        *reinterpret_cast<uint4*>(dgimg + tile_img_offset(itok, 16, (2 * 4 + ub) * 64 + cin)) = o_hn;
                         *reinterpret_cast<uint4*>(dgimg + tile_img_offset(itok, 16, (3 * 4 + ub) * 64 + cin)) = pack8bf(gan);
+                    }
+                    if (t + 1 < L) {
+                        // the MMAs of the previous unit block must have consumed the A stage (they finished
+                        // long ago: this chunk's math alone takes longer than a block's MMAs)
+                        if (c8 == 0) mbar_wait(&a_empty, (ait & 1) ^ 1);
+                        const uint32_t so = sw128_offset(BT_M, rl, hf * 32 + c8 * 8);
+                        *reinterpret_cast<uint4*>(sA + 0 * BT_ACHUNK + so) = o_r;
+                        *reinterpret_cast<uint4*>(sA + 1 * BT_ACHUNK + so) = o_z;
+                        *reinterpret_cast<uint4*>(sA + 2 * BT_ACHUNK + so) = o_hn;
+                        *reinterpret_cast<uint4*>(sA + 3 * BT_ACHUNK + so) = pack8bf(czh);
+                        *reinterpret_cast<uint4*>(sA + 4 * BT_ACHUNK + so) = pack8bf(czl);
                     }
                 }
                 if (t + 1 < L) {
-                    // the MMAs of the previous unit block must have consumed the A stage
-                    mbar_wait(&a_empty, (ait & 1) ^ 1);
-#pragma unroll
-                    for (int c = 0; c < 5; ++c)
-#pragma unroll
-                        for (int c8 = 0; c8 < 4; ++c8)
-                            *reinterpret_cast<uint4*>(sA + c * BT_ACHUNK + sw128_offset(BT_M, rl, hf * 32 + c8 * 8)) = outA[c][c8];
                     fence_proxy_async_smem();
                     tc_fence_before();
                     __syncwarp();
