@@ -190,7 +190,7 @@ def run_ours(a):
     clocks = ClockSampler(local) if rank == 0 else None
     if clocks:
         clocks.start()
-    _lib.reset_counters(profile=True)
+    _lib.reset_counters(profile=False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -200,6 +200,23 @@ def run_ours(a):
     barrier()
     dev_ms = e0.elapsed_time(e1)
     launches = _lib.kernel_launches()
+
+    # ---- per-kernel CUDA-event times for the roofline / shares: same steps, but the mini-batches run one
+    #      after the other on one stream so that every launch is timed without a concurrent neighbour ----
+    def one_step_serial(rng, train_state, agents, vcs, buf):
+        rng, _rng = prng.split(rng, 2)
+        train_state, agents, vcs, metrics = step_fn(rng=_rng, lpg_train_state=train_state, agent_states=agents,
+                                                    value_critic_states=vcs, num_streams=1)
+        rng, _rng = prng.split(rng, 2)
+        buf, agents, vcs = sampler.sample(_rng, buf, agents, vcs)
+        return rng, train_state, agents, vcs, buf, metrics
+    PROF_STEPS = 2
+    *state, metrics = one_step_serial(*state)
+    barrier()
+    _lib.reset_counters(profile=True)
+    for _ in range(PROF_STEPS):
+        *state, metrics = one_step_serial(*state)
+    barrier()
     prof = _lib.profile_ms()
     _lib.reset_counters(profile=False)
 
@@ -237,23 +254,25 @@ def run_ours(a):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    tokens = AGENTS_PER_GPU * W * L
+    per_launch_agents = AGENTS_PER_GPU // mini_batches
+    tokens = per_launch_agents * W * L
     flops = {   # algorithmic FLOPs per launch
         "toued_gru_forward": tokens * 400896.0,
-        "toued_gru_backward": AGENTS_PER_GPU * W * (L - 1) * 2.0 * 768 * 256 + tokens * 2.0 * 256 * 9,
+        "toued_gru_backward": per_launch_agents * W * (L - 1) * 2.0 * 768 * 256 + tokens * 2.0 * 256 * 9,
         "toued_lpg_wgrad": tokens * (2.0 * 256 * 768 + 2.0 * 8 * 768 + 2.0 * 256 * 9),
         "toued_gru_forward_tc": tokens * 400896.0,
-        "toued_gru_backward_tc": AGENTS_PER_GPU * W * (L - 1) * 2.0 * (768 + 2 * 64) * 256 + tokens * 2.0 * 256 * 9,
+        "toued_gru_backward_tc": per_launch_agents * W * (L - 1) * 2.0 * (768 + 2 * 64) * 256 + tokens * 2.0 * 256 * 9,
         "toued_lpg_wgrad_tc": tokens * (2.0 * 256 * 768 + 2.0 * 8 * 768 + 2.0 * 256 * 9),
     }
     total_prof = sum(ms for _, ms in prof.values()) or 1.0
-    shares = {k: {"calls": c, "ms_per_step": ms / a.steps, "share": ms / total_prof} for k, (c, ms) in prof.items()}
+    shares = {k: {"calls": c, "ms_per_step": ms / PROF_STEPS, "share": ms / total_prof} for k, (c, ms) in prof.items()}
     dom = max((k for k in prof if k in flops), key=lambda k: prof[k][1])
     calls, ms = prof[dom]
     achieved = flops[dom] / (ms / calls * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": None, "agents_per_launch": per_launch_agents,
+                "ms_per_launch": ms / calls,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback",
                 "note": ("tcgen05 path (fp16/bf16 operands, fp32 accumulate in TMEM)" if precision == "tc" else
                          "exact-fp32 SIMT GRU path") + "; FLOPs = algorithmic GRU/head/weight-gradient FLOPs per launch"}

@@ -359,15 +359,19 @@ embed_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
                       const float* __restrict__ critic, const float* __restrict__ lpg, int emb_off,
                       const float* __restrict__ dx, float* __restrict__ partial, int n_agents, int W, int L, int D,
                       int accumulate) {
+    // phase 1: each thread back-propagates its token through the two embedding-MLP applications and leaves
+    //          (y[8], da[16], relu(a)*dp [16], dp) in shared memory; phase 2: thread o < 161 owns one parameter
+    //          and sums its products over the block's 2 x 256 samples (fixed order -> deterministic).
+    constexpr int SREC = LPG_Y + 2 * LPG_E + 1;            // 41 floats per sample
     __shared__ float sp[EM_TOTAL];
-    __shared__ float sacc[8][EM_TOTAL];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ __align__(16) float srec[];          // [2 * 256][41] = 82 KB (dynamic)
+    const int tid = threadIdx.x;
     for (int i = tid; i < EM_TOTAL; i += 256) sp[i] = lpg[emb_off + i];
-    for (int i = tid; i < 8 * EM_TOTAL; i += 256) (&sacc[0][0])[i] = 0.f;
     __syncthreads();
     const size_t total = (size_t)n_agents * L * W;
     const size_t R = (size_t)n_agents * W;
     const size_t iters = (total + (size_t)gridDim.x * 256 - 1) / ((size_t)gridDim.x * 256);
+    float acc = 0.0f;                                      // this thread's parameter (tid < 161)
     for (size_t it = 0; it < iters; ++it) {
         const size_t g = (it * gridDim.x + blockIdx.x) * 256 + tid;
         const bool ok = g < total;
@@ -390,38 +394,39 @@ embed_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
         }
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            float da[LPG_E], ra[LPG_E];
+            float* r = srec + (size_t)(s * 256 + tid) * SREC;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = y[s][i];
 #pragma unroll
             for (int e = 0; e < LPG_E; ++e) {
                 float a = sp[LPG_Y * LPG_E + e];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) a = fmaf(y[s][i], sp[i * LPG_E + e], a);
-                ra[e] = fmaxf(a, 0.0f);
-                da[e] = a > 0.0f ? dp[s] * sp[LPG_Y * LPG_E + LPG_E + e] : 0.0f;
+                r[8 + e] = a > 0.0f ? dp[s] * sp[LPG_Y * LPG_E + LPG_E + e] : 0.0f;     // da_e
+                r[8 + LPG_E + e] = fmaxf(a, 0.0f) * dp[s];                               // relu(a_e) * dp
             }
-            // warp-reduce each of the 161 contributions, lane 0 accumulates into its warp's row
-            auto red = [&](int idx, float v) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) sacc[warp][idx] += v;
-            };
-#pragma unroll
-            for (int e = 0; e < LPG_E; ++e) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) red(i * LPG_E + e, y[s][i] * da[e]);
-                red(LPG_Y * LPG_E + e, da[e]);
-                red(LPG_Y * LPG_E + LPG_E + e, ra[e] * dp[s]);
-            }
-            red(LPG_Y * LPG_E + 2 * LPG_E, dp[s]);
+            r[8 + 2 * LPG_E] = dp[s];
         }
+        __syncthreads();
+        if (tid < EM_TOTAL) {
+            // parameter tid: e_w0[i][e] -> y_i * da_e ; e_b0[e] -> da_e ; e_w1[e] -> relu(a_e) dp ; e_b1 -> dp
+            int ia = -1, ib;
+            if (tid < LPG_Y * LPG_E) { ia = tid / LPG_E; ib = 8 + tid % LPG_E; }
+            else if (tid < LPG_Y * LPG_E + LPG_E) ib = 8 + (tid - LPG_Y * LPG_E);
+            else if (tid < LPG_Y * LPG_E + 2 * LPG_E) ib = 8 + LPG_E + (tid - LPG_Y * LPG_E - LPG_E);
+            else ib = 8 + 2 * LPG_E;
+            float a_ = 0.0f;
+            for (int q = 0; q < 512; ++q) {
+                const float* r = srec + (size_t)q * SREC;
+                a_ = fmaf(ia >= 0 ? r[ia] : 1.0f, r[ib], a_);
+            }
+            acc += a_;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = tid; i < EM_TOTAL; i += 256) {
-        float v = 0.f;
-#pragma unroll
-        for (int wq = 0; wq < 8; ++wq) v += sacc[wq][i];
-        float* o = partial + (size_t)blockIdx.x * EM_TOTAL + i;
-        *o = accumulate ? *o + v : v;
+    if (tid < EM_TOTAL) {
+        float* o = partial + (size_t)blockIdx.x * EM_TOTAL + tid;
+        *o = accumulate ? *o + acc : acc;
     }
 }
 
@@ -429,6 +434,7 @@ constexpr int WG_SPLITS = 37;        // token splits of the dWh GEMM (SIMT uses 
 constexpr int WG_SPLITS_SIMT = 32;
 constexpr int SM_SPLITS = 592;       // 4 per SM for the streaming kernels
 constexpr int EM_SPLITS = 296;
+constexpr int EM_SMEM = 2 * 256 * (LPG_Y + 2 * LPG_E + 1) * (int)sizeof(float);
 
 extern "C" int toued_lpg_wgrad_workspace_floats(void) {
     return WG_SPLITS * LPG_H * LPG_G + SM_SPLITS * SM_TOTAL + EM_SPLITS * EM_TOTAL;
@@ -457,7 +463,8 @@ extern "C" int toued_lpg_wgrad(const int32_t* obs, const uint8_t* done, const fl
         wgrad_small_kernel<<<SM_SPLITS, 256, 0, st>>>(x, h, dgates, d_pi_hat, dl, p_sm, R, L, tps, accumulate);
         TOUED_LAUNCH_CHECK();
     }
-    embed_backward_kernel<<<EM_SPLITS, 256, 0, st>>>(obs, done, critic, lpg_params, lpg_offsets(lifetime_conditioning ? 7 : 5).e_w0,
+    TOUED_CUDA(cudaFuncSetAttribute(embed_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EM_SMEM));
+    embed_backward_kernel<<<EM_SPLITS, 256, EM_SMEM, st>>>(obs, done, critic, lpg_params, lpg_offsets(lifetime_conditioning ? 7 : 5).e_w0,
                                                       dx, p_em, n_agents, n_workers, L, obs_dim, accumulate);
     TOUED_LAUNCH_CHECK();
     return 0;
@@ -510,7 +517,8 @@ extern "C" int toued_lpg_wgrad_embed(const int32_t* obs, const uint8_t* done, co
                                      const float* dx, float* workspace, int n_agents, int n_workers, int rollout_len,
                                      int obs_dim, int lifetime_conditioning, int accumulate, void* stream) {
     float* p_em = workspace + toued_lpg_wgrad_workspace_offset(2);
-    embed_backward_kernel<<<EM_SPLITS, 256, 0, (cudaStream_t)stream>>>(
+    TOUED_CUDA(cudaFuncSetAttribute(embed_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EM_SMEM));
+    embed_backward_kernel<<<EM_SPLITS, 256, EM_SMEM, (cudaStream_t)stream>>>(
         obs, done, critic, lpg_params, lpg_offsets(lifetime_conditioning ? 7 : 5).e_w0, dx, p_em, n_agents, n_workers,
         rollout_len, obs_dim, accumulate);
     TOUED_LAUNCH_CHECK();

@@ -84,6 +84,13 @@ def _workspace(n, w, L, D, K, P, device, slot=0) -> MetaGradWorkspace:
     return ws
 
 
+def _eval_stream(device):
+    key = ("eval", str(device))
+    if key not in _STREAMS:
+        _STREAMS[key] = [torch.cuda.Stream(device=device)]
+    return _STREAMS[key][0]
+
+
 def _side_streams(device, n):
     key = str(device)
     lst = _STREAMS.setdefault(key, [])
@@ -154,6 +161,8 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     returns = torch.empty(N, dtype=torch.float32, device=dev)
     ready = torch.cuda.Event()
     ready.record(main)
+    eval_done = [None] * S
+    eval_stream = _side_streams(dev, S + 1)[S] if S > 1 else _eval_stream(dev)
 
     for mb in range(num_mini_batches):
         slot = mb % S
@@ -161,6 +170,8 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
         with torch.cuda.stream(streams[slot]):
             if S > 1 and mb < S:
                 streams[slot].wait_event(ready)
+            if eval_done[slot] is not None:           # the previous chunk on this workspace is still being evaluated
+                streams[slot].wait_event(eval_done[slot])
             s = _lib.stream_ptr()
             if mb < S:
                 if tc:
@@ -183,6 +194,15 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                       p(tape.action[K]), p(tape.reward[K]), p(tape.done[K]), None, nb, W, L, D,
                       env.max_grid_size, env.max_n_objs, 0, s)
             _lib.call("toued_sort_tokens", p(tape.obs[K]), p(tape.sorted_tok[K]), nb, W, L, s)
+            # ---- evaluate agent return: 4 workers, metric only (meta/train.py:109-117, Q11).  A long, thin
+            #      kernel (max_rollout_len sequential steps): it runs on its own stream next to the reverse pass.
+            fwd_done = torch.cuda.Event()
+            fwd_done.record(streams[slot])
+            with torch.cuda.stream(eval_stream):
+                eval_stream.wait_event(fwd_done)
+                returns[sl] = eval_agent(r_evalagent[sl], rollout_manager, levels, tape.actor[K], eval_workers)
+                eval_done[slot] = torch.cuda.Event()
+                eval_done[slot].record(eval_stream)
             # ---- value "update" (Q2) + advantage + LPG loss + lam_K (meta/train.py:60-100) ----
             vparams = value_critic_states.params[sl]
             _lib.call("toued_meta_loss", p(tape.obs[K]), p(tape.action[K]), p(tape.reward[K]), p(tape.done[K]),
@@ -225,13 +245,10 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
             new_step[sl] = sub2.actor_state.step
             new_state[sl] = state
             new_obs[sl] = tape.obs[K][:, -1]
-            # ---- evaluate agent return: 4 workers, metric only (meta/train.py:109-117, Q11) ----
-            returns[sl] = eval_agent(r_evalagent[sl], rollout_manager, levels, tape.actor[K], eval_workers)
-    if S > 1:
-        for st in streams:
-            ev = torch.cuda.Event()
-            ev.record(st)
-            main.wait_event(ev)
+    for st in ([] if S == 1 else list(streams)) + [eval_stream]:
+        ev = torch.cuda.Event()
+        ev.record(st)
+        main.wait_event(ev)
     s = _lib.stream_ptr()
     msum = msums[0] if S == 1 else torch.stack(msums).sum(0)
 
