@@ -194,14 +194,17 @@ int toued_masked_reset(const void* levels, const uint8_t* mask, int32_t* state, 
 /* Unit check of the tcgen05 building blocks: D f32[128][48] = A f32[128][256] * B f32[48][256]^T with
  * fp16 operands / fp32 accumulation in TMEM.  scratch_img: 24 KiB device scratch.                  */
 int toued_tc_gemm_test(const float* A, const float* B, void* scratch_img, float* D, void* stream);
+/* Same with K = 256 + 16: the last 16 K-columns live in no-swizzle K-major tiles (the layout of the
+ * input-projection block of the GRU forward).  A f32[128][272], B f32[48][272]; scratch_img 32 KiB.   */
+int toued_tc_gemm_mixed_test(const float* A, const float* B, void* scratch_img, float* D, void* stream);
 /* Same for MN-major bf16 operands from token tile images: D f32[128][128] = A f32[128 k][128]^T * B f32[128 k][128]
  * (the weight-gradient GEMM shape).  scratch_img: 64 KiB.                                           */
 int toued_tc_gemm_mn_test(const float* A, const float* B, void* scratch_img, float* D, int lbo, int sbo,
                           int kadv, void* stream);
 
-/* Pack the recurrent matrix Wh into the fp16 SW128 pass images the tensor-core forward streams
- * (wh_img: 384 KiB, once per meta-step).                                                           */
-int toued_pack_wh_forward(const float* lpg_params, void* wh_img, void* stream);
+/* Pack the recurrent matrix Wh (+ input projection Wi, b_i) into the fp16 pass images the tensor-core
+ * forward streams (wh_img: 16 x 26 KiB = 416 KiB, once per meta-step).                              */
+int toued_pack_wh_forward(const float* lpg_params, void* wh_img, int lifetime_conditioning, void* stream);
 /* Tensor-core version of toued_gru_forward (models/lpg.py:11-30,77-84): fp16 operands, fp32
  * accumulation in TMEM.  Saved for the reverse pass (NULL to skip):
  *   h16   f16, RB32 layout [L][ceil(R/32)][32 chunks][32 rows][8 units] (csrc/tc.cuh::rb32_index)   h_t

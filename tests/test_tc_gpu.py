@@ -22,6 +22,22 @@ def test_tcgen05_gemm_tile(built_lib):
     assert err < 2e-4, f"tcgen05 tile mismatch: max abs err {err}"
 
 
+def test_tcgen05_mixed_swizzle_k_blocks(built_lib):
+    """K = 256 in SW128 blocks + 16 in a no-swizzle K-major block within one accumulation chain."""
+    from to_ued_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(2)
+    A = torch.randn(128, 272, generator=g)
+    B = torch.randn(48, 272, generator=g)
+    Ad, Bd = A.cuda(), B.cuda()
+    img = torch.zeros(32768, dtype=torch.uint8, device="cuda")
+    D = torch.zeros(128, 48, device="cuda")
+    _lib.call("toued_tc_gemm_mixed_test", _lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(img), _lib.ptr(D), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    want = A.half().double() @ B.half().double().T
+    err = (D.cpu().double() - want).abs().max().item()
+    assert err < 2e-4, f"mixed-swizzle tcgen05 tile mismatch: max abs err {err}"
+
+
 def test_tcgen05_mn_major_gemm_tile(built_lib):
     from to_ued_b200 import _lib
     g = torch.Generator(device="cpu").manual_seed(1)
@@ -68,7 +84,7 @@ def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond):
                   p(ag.actor_state.params), p(ag.critic_state.params), p(lpg), p(ag.actor_state.step),
                   p(ag.level.packed), p(tape.x[0]), None, n, c.w, c.L, c.D, int(cond), 0, s)
         if prec == "tc":
-            _lib.call("toued_pack_wh_forward", p(lpg), p(tape.wh_img), s)
+            _lib.call("toued_pack_wh_forward", p(lpg), p(tape.wh_img), int(cond), s)
             _lib.call("toued_gru_forward_tc", p(tape.x[0]), p(tape.done[0]), p(lpg), p(tape.wh_img), p(tape.h16[0]),
                       p(tape.fac[0]), p(tape.hpimg[0]), p(tape.pi_hat[0]), p(tape.y_hat[0]), n, c.w, c.L, int(cond), s)
             R = n * c.w

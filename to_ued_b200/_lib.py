@@ -63,8 +63,9 @@ SIGNATURES = {
     "toued_init_tables": [_P] * 3 + [_I] * 3 + [_P],
     "toued_masked_reset": [_P] * 5 + [_I] * 3 + [_P],
     "toued_tc_gemm_test": [_P] * 5,
+    "toued_tc_gemm_mixed_test": [_P] * 5,
     "toued_tc_gemm_mn_test": [_P] * 4 + [_I] * 3 + [_P],
-    "toued_pack_wh_forward": [_P] * 3,
+    "toued_pack_wh_forward": [_P, _P, _I, _P],
     "toued_gru_forward_tc": [_P] * 9 + [_I] * 4 + [_P],
 }
 

@@ -72,7 +72,7 @@ class Tape:
             # bf16 token-tile images (rows >= R of a partial 64-token block stay zero)
             self.hpimg = torch.zeros((ka, L * Rp * 256 * 2), dtype=torch.uint8, device=dev) if self.record else None
             self.ximg = torch.zeros((ka, L * Rp * 128), dtype=torch.uint8, device=dev) if self.record else None
-            self.wh_img = torch.empty(256 * 768, dtype=f16, device=dev)
+            self.wh_img = torch.zeros(16 * 26624 // 2, dtype=f16, device=dev)      # 16 pass images of 26 KiB
             self.h = self.gates = None
         else:
             self.h = torch.empty((ka, L, R, 256), dtype=f32, device=dev)
@@ -158,7 +158,7 @@ def train_lpg_agent(rng, lpg_train_state, agent_state: AgentState, rollout_manag
     lpg = lpg_train_state.params if hasattr(lpg_train_state, "params") else lpg_train_state
     cond = lpg_train_state.model.lifetime_conditioning if hasattr(lpg_train_state, "model") else False
     if tape.precision == "tc" and not lpg_stride:             # recurrent matrix -> fp16 SW128 pass images
-        _lib.call("toued_pack_wh_forward", p(lpg), p(tape.wh_img), s)
+        _lib.call("toued_pack_wh_forward", p(lpg), p(tape.wh_img), int(cond), s)
     for k in range(K):
         r = tape.ri(k)
         _lib.call("toued_rollout", p(levels), p(keys_d[k]), p(tape.actor[tape.ti(k)]), None, p(state), p(tape.obs[r]),

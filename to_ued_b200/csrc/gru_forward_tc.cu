@@ -6,10 +6,14 @@
 //   * the recurrent matrix is pre-packed once per meta-step into fp16 SW128 "pass" images
 //     (16 passes x [3 gates x 16 units = 48 rows][256 k] = 24 KB each) and streamed from L2 by a
 //     TMA-producer warp (cp.async.bulk + mbarrier, 2 stages);
-//   * one elected thread issues tcgen05.mma (M128 N48 K16, 16 per pass) into a double-buffered TMEM
+//   * the input projection x W_i + b_i rides in the same GEMM as a 17th K-step: a no-swizzle K = 16 block
+//     holding x_t (fp16, slot 7 = 1 for the bias); its MMA (N = 64) runs first and initialises the
+//     accumulator columns (r | z | 0 | i_n), the recurrent MMAs (N = 48) accumulate onto (r | z | h_n)
+//     — i_n stays separate because r gates only the hidden part of the candidate;
+//   * one elected thread issues tcgen05.mma (M128 K16, 17 per pass) into a double-buffered TMEM
 //     accumulator and commits to mbarriers;
-//   * 8 epilogue warps tcgen05.ld the three gate pre-activations of their (row, 8 units), add the fp32
-//     input projection x W_i + b_i, apply the flax GRUCell gate math, write h_t (fp16) into A[nxt] and
+//   * 8 epilogue warps tcgen05.ld the four gate pre-activations of their (row, 8 units),
+//     apply the flax GRUCell gate math, write h_t (fp16) into A[nxt] and
 //     h (fp16), the five reverse-pass factors (fp16) and the masked carry h' (bf16 tile image) to HBM, and accumulate the two heads
 //     (pi_hat, y_hat logits) on relu(h_t) in registers.
 // fp16 operands / fp32 accumulate: the hidden state is quantised to fp16 once per step (|h| < 1).
@@ -23,7 +27,11 @@ constexpr int FT_PU = 16;                 // hidden units per pass
 constexpr int FT_PN = 3 * FT_PU;          // 48 accumulator columns per pass
 constexpr int FT_NPASS = LPG_H / FT_PU;   // 16
 constexpr int FT_KB = LPG_H / 64;         // 4 K-blocks
-constexpr int FT_BSTAGE = FT_KB * FT_PN * 128;     // 24576 B per pass image
+constexpr int FT_BH = FT_KB * FT_PN * 128;         // 24576 B: recurrent part of a pass image (SW128 K-blocks)
+constexpr int FT_XN = 64;                          // x-part rows: Wi_r, Wi_z, 0, Wi_n (16 each) -> accumulator cols 0..63
+constexpr int FT_BX = (FT_XN / 8) * 256;           // 2048 B: input part (no-swizzle K=16 block: x[0..7] incl. the bias 1)
+constexpr int FT_BSTAGE = FT_BH + FT_BX;           // 26624 B per pass image (multiple of 1024)
+constexpr int FT_AX = (FT_M / 8) * 256;            // 4096 B: x tile of the A operand
 constexpr int FT_ABUF = FT_KB * FT_M * 128;        // 65536 B
 constexpr int FT_NS = 2;                  // B stages
 constexpr int FT_THREADS = 320;           // 8 epilogue warps + producer warp + MMA warp
@@ -38,9 +46,30 @@ __global__ void pack_wh_fwd_kernel(const float* __restrict__ Wh, __half* __restr
     *reinterpret_cast<__half*>(base + sw128_offset(FT_PN, g * FT_PU + u, k)) = __float2half_rn(Wh[i]);
 }
 
-extern "C" int toued_pack_wh_forward(const float* lpg_params, void* wh_img, void* stream) {
+// input part of the pass images: rows [0,16) Wi_r, [16,32) Wi_z, [32,48) zero, [48,64) Wi_n of the pass's
+// 16 units; k = input index (k < X: Wi[k], k == 7: bias b_i, else 0)
+__global__ void pack_wi_fwd_kernel(const float* __restrict__ lpg, int X, __half* __restrict__ img) {
+    const LpgOffsets o = lpg_offsets(X);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= FT_NPASS * FT_XN * 16) return;
+    const int k = i & 15, row = (i >> 4) % FT_XN, p = i / (16 * FT_XN);
+    const int blk = row >> 4, u = p * FT_PU + (row & 15);
+    float v = 0.0f;
+    if (blk != 2) {
+        const int g = blk == 3 ? 2 : blk;
+        if (k < X) v = lpg[o.Wi + k * LPG_G + g * LPG_H + u];
+        else if (k == 7) v = lpg[o.bi + g * LPG_H + u];
+    }
+    char* base = reinterpret_cast<char*>(img) + (size_t)p * FT_BSTAGE + FT_BH;
+    *reinterpret_cast<__half*>(base + k16_offset(row, k)) = __float2half_rn(v);
+}
+
+extern "C" int toued_pack_wh_forward(const float* lpg_params, void* wh_img, int lifetime_conditioning, void* stream) {
+    const int X = lifetime_conditioning ? 7 : 5;
     pack_wh_fwd_kernel<<<(LPG_H * LPG_G + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        lpg_params + lpg_offsets(5).Wh, (__half*)wh_img);
+        lpg_params + lpg_offsets(X).Wh, (__half*)wh_img);
+    TOUED_LAUNCH_CHECK();
+    pack_wi_fwd_kernel<<<(FT_NPASS * FT_XN * 16 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(lpg_params, X, (__half*)wh_img);
     TOUED_LAUNCH_CHECK();
     return 0;
 }
@@ -53,10 +82,10 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                       float* __restrict__ pi_hat, float* __restrict__ y_hat, int R, int L, int W) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* sA = smem;                                   // 2 x 64 KB
-    unsigned char* sB = sA + 2 * FT_ABUF;                       // FT_NS x 24 KB
-    float* sWi = reinterpret_cast<float*>(sB + FT_NS * FT_BSTAGE);   // [256 units][3 gates][8]: Wi rows 0..X-1, 0.., bias in slot 7
-    float* sbhn = sWi + LPG_H * 24;                             // [256]
+    unsigned char* sA = smem;                                   // 2 x 64 KB   h' (SW128 K-blocks)
+    unsigned char* sAx = sA + 2 * FT_ABUF;                      // 2 x 4 KB    x tile (no-swizzle K = 16 block)
+    unsigned char* sB = sAx + 2 * FT_AX;                        // FT_NS x 26 KB
+    float* sbhn = reinterpret_cast<float*>(sB + FT_NS * FT_BSTAGE);   // [256]
     float* swp = sbhn + LPG_H;                                  // [256]
     float* sWy = swp + LPG_H;                                   // [256][8]
     float* shead = sWy + LPG_H * LPG_Y;                         // [128][9] partial heads of the hf=1 half
@@ -74,14 +103,25 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
         mbar_fence_init();
     }
     if (warp == 9) tmem_alloc(&tmem_base_s, 128);
-    for (int i = tid; i < LPG_H * 24; i += FT_THREADS) {
-        const int u = i / 24, g = (i % 24) >> 3, q = i & 7;
-        sWi[i] = q < X ? lpg[o.Wi + q * LPG_G + g * LPG_H + u] : (q == 7 ? lpg[o.bi + g * LPG_H + u] : 0.0f);
-    }
+
     for (int i = tid; i < LPG_H; i += FT_THREADS) { sbhn[i] = lpg[o.bhn + i]; swp[i] = lpg[o.w_pi + i]; }
     for (int i = tid; i < LPG_H * LPG_Y; i += FT_THREADS) sWy[i] = lpg[o.W_y + i];
-    // initial carry = 0 (both A buffers)
-    for (int i = tid; i < 2 * FT_ABUF / 16; i += FT_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // initial carry = 0 (both A buffers); x tiles zero (columns 8..15 stay zero), then x_{L-1} into tile 0
+    for (int i = tid; i < (2 * FT_ABUF + 2 * FT_AX) / 16; i += FT_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    if (tid < FT_M) {
+        const int r_ = row0 + tid;
+        if (r_ < R) {
+            const float4* xp = reinterpret_cast<const float4*>(x + ((size_t)(L - 1) * R + r_) * LPG_XP);
+            const float4 x0 = xp[0], x1 = xp[1];
+            __half2 h0 = __floats2half2_rn(x0.x, x0.y), h1 = __floats2half2_rn(x0.z, x0.w);
+            __half2 h2 = __floats2half2_rn(x1.x, x1.y), h3 = __floats2half2_rn(x1.z, x1.w);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(sAx + k16_offset(tid, 0)) = pk;
+        }
+    }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -105,13 +145,14 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
     } else if (warp == 9) {
         // ===================== MMA issuer ==========================================================
         if (lane == 0) {
-            constexpr uint32_t idesc = tc_idesc(FT_M, FT_PN, 0);
+            constexpr uint32_t idesc = tc_idesc(FT_M, FT_PN, 0), idesc_x = tc_idesc(FT_M, FT_XN, 0);
             uint32_t it = 0;
             int cur = 0;
             for (int t = L - 1, step = 0; t >= 0; --t, ++step) {
                 if (step > 0) { mbar_wait(&a_ready, (step - 1) & 1); }
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + cur * FT_ABUF);
+                const uint64_t axd = tc_smem_desc_k16(smem_u32(sAx + cur * FT_AX));
                 for (int p = 0; p < FT_NPASS; ++p, ++it) {
                     const int s = it % FT_NS, a = it & 1;
                     mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
@@ -119,12 +160,15 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                     tc_fence_after();
                     const uint32_t b_addr = smem_u32(sB + s * FT_BSTAGE);
                     const uint32_t d_addr = tmem_base + a * 64;
+                    // input projection + bias first: initialises all 64 accumulator columns
+                    // (r | z | 0 | i_n); the recurrent part then accumulates onto columns 0..47 (r | z | h_n)
+                    tc_mma(d_addr, axd, tc_smem_desc_k16(b_addr + FT_BH), idesc_x, 0u);
 #pragma unroll
                     for (int kb = 0; kb < FT_KB; ++kb) {
                         const uint64_t ad = tc_smem_desc(a_addr + kb * FT_M * 128);
                         const uint64_t bd = tc_smem_desc(b_addr + kb * FT_PN * 128);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) tc_mma(d_addr, ad + 2 * ks, bd + 2 * ks, idesc, (kb | ks) != 0);
+                        for (int ks = 0; ks < 4; ++ks) tc_mma(d_addr, ad + 2 * ks, bd + 2 * ks, idesc, 1u);
                     }
                     tc_commit(&b_empty[s]);
                     tc_commit(&acc_full[a]);
@@ -146,13 +190,18 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
         uint32_t it = 0;
         int cur = 0;
         for (int t = L - 1; t >= 0; --t) {
-            float xr[8];                                       // x row; slot 7 is the constant 1 (bias)
-            {
-                const float4* xp = reinterpret_cast<const float4*>(x + ((size_t)t * R + rsafe) * LPG_XP);
-                const float4 x0 = xp[0], x1 = xp[1];
-                const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) xr[i] = rv ? xa[i] : 0.0f;
+            // x_{t-1} (the next processed step) goes into the other x tile as fp16 (one thread per row)
+            if (hf == 0 && t > 0) {
+                uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                if (rv) {
+                    const float4* xp = reinterpret_cast<const float4*>(x + ((size_t)(t - 1) * R + row) * LPG_XP);
+                    const float4 x0 = xp[0], x1 = xp[1];
+                    __half2 h0 = __floats2half2_rn(x0.x, x0.y), h1 = __floats2half2_rn(x0.z, x0.w);
+                    __half2 h2 = __floats2half2_rn(x1.x, x1.y), h3 = __floats2half2_rn(x1.z, x1.w);
+                    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                }
+                *reinterpret_cast<uint4*>(sAx + (cur ^ 1) * FT_AX + k16_offset(rl, 0)) = pk;
             }
             // mask for the NEXT processed step (t-1): its carry is zero where done[t-1]
             const bool zero_next = (t > 0) && done[((size_t)n_ag * L + (t - 1)) * W + w_ag];
@@ -166,11 +215,12 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                 const int a = it & 1;
                 mbar_wait(&acc_full[a], (it >> 1) & 1);
                 tc_fence_after();
-                float ar[8], az[8], an[8];
+                float ar[8], az[8], an[8], ai[8];
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a * 64 + hf * 8;
                 tmem_ld8(ta, ar);
                 tmem_ld8(ta + FT_PU, az);
                 tmem_ld8(ta + 2 * FT_PU, an);
+                tmem_ld8(ta + 3 * FT_PU, ai);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -186,22 +236,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int u = u0 + e;
-                    float gr = ar[e], gz = az[e], gn = 0.0f;
-                    {
-                        const float4* wv = reinterpret_cast<const float4*>(sWi + u * 24);     // warp-broadcast loads
-                        const float4 r0 = wv[0], r1 = wv[1], z0 = wv[2], z1 = wv[3], n0 = wv[4], n1 = wv[5];
-                        gr = fmaf(xr[0], r0.x, gr); gr = fmaf(xr[1], r0.y, gr); gr = fmaf(xr[2], r0.z, gr); gr = fmaf(xr[3], r0.w, gr);
-                        gr = fmaf(xr[4], r1.x, gr); gr = fmaf(xr[7], r1.w, gr);
-                        gz = fmaf(xr[0], z0.x, gz); gz = fmaf(xr[1], z0.y, gz); gz = fmaf(xr[2], z0.z, gz); gz = fmaf(xr[3], z0.w, gz);
-                        gz = fmaf(xr[4], z1.x, gz); gz = fmaf(xr[7], z1.w, gz);
-                        gn = fmaf(xr[0], n0.x, gn); gn = fmaf(xr[1], n0.y, gn); gn = fmaf(xr[2], n0.z, gn); gn = fmaf(xr[3], n0.w, gn);
-                        gn = fmaf(xr[4], n1.x, gn); gn = fmaf(xr[7], n1.w, gn);
-                        if (X > 5) {
-                            gr = fmaf(xr[5], r1.y, gr); gr = fmaf(xr[6], r1.z, gr);
-                            gz = fmaf(xr[5], z1.y, gz); gz = fmaf(xr[6], z1.z, gz);
-                            gn = fmaf(xr[5], n1.y, gn); gn = fmaf(xr[6], n1.z, gn);
-                        }
-                    }
+                    const float gr = ar[e], gz = az[e], gn = ai[e];      // input projection + bias already inside
                     const float rr = sigmoid_fast(gr);
                     zz[e] = sigmoid_fast(gz);
                     const float hn = an[e] + sbhn[u];
@@ -291,7 +326,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
 
 static size_t gru_fwd_tc_smem(int X) {
     (void)X;
-    return 2 * FT_ABUF + FT_NS * FT_BSTAGE + sizeof(float) * (LPG_H * 24 + 2 * LPG_H + LPG_H * LPG_Y + FT_M * 9) + 1024;
+    return 2 * FT_ABUF + 2 * FT_AX + FT_NS * FT_BSTAGE + sizeof(float) * (2 * LPG_H + LPG_H * LPG_Y + FT_M * 9) + 1024;
 }
 
 extern "C" int toued_gru_forward_tc(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,

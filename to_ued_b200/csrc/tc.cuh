@@ -42,6 +42,16 @@ __host__ __device__ __forceinline__ size_t rb32_index(size_t t, size_t n_row_blo
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// K-major, NO swizzle ("interleave") operand for a narrow K = 16 block: 8-row x 16-byte core matrices
+// (128 B contiguous); the second 8-element K chunk is `lbo` bytes further, the next 8-row group `sbo`
+// bytes further.  byte offset of element (row, k), k < 16, with lbo = 128, sbo = 256:
+__host__ __device__ __forceinline__ uint32_t k16_offset(int row, int k) {
+    return (uint32_t)(row >> 3) * 256u + (uint32_t)(k >> 3) * 128u + (uint32_t)(row & 7) * 16u + (uint32_t)(k & 7) * 2u;
+}
+__device__ __forceinline__ uint64_t tc_smem_desc_k16(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) |
+           (1ull << 46);                                   // layout type 0 = no swizzle
+}
 // MN-major SW128 operand (contraction index = rows of the tile image): 64 MN-elements (128 B) per k-row,
 // 8 k-rows per 1024-byte swizzle atom (SBO), next group of 64 MN-elements `lbo_bytes` away (LBO).
 __device__ __forceinline__ uint64_t tc_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {

@@ -153,3 +153,78 @@ extern "C" int toued_tc_gemm_mn_test(const float* A, const float* B, void* scrat
     TOUED_LAUNCH_CHECK();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// K = 256 (SW128 blocks) + 16 (no-swizzle block): D[128][48] = A[128][272] * B[48][272]^T, fp16.
+__global__ void pack_b_mixed_kernel(const float* __restrict__ B, __half* __restrict__ img, int N, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * K) return;
+    const int n = i / K, k = i % K;
+    char* base = reinterpret_cast<char*>(img);
+    if (k < 256) *reinterpret_cast<__half*>(base + sw128_offset(N, n, k)) = __float2half_rn(B[i]);
+    else *reinterpret_cast<__half*>(base + 4 * N * 128 + k16_offset(n, k - 256)) = __float2half_rn(B[i]);
+}
+
+__global__ void __launch_bounds__(128, 1)
+tc_gemm_mixed_test_kernel(const float* __restrict__ A, const __half* __restrict__ Bimg, float* __restrict__ D) {
+    constexpr int N = 48, K = 272;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sA = smem;                               // 4 x 16 KB SW128 + 4 KB k16 tile
+    unsigned char* sAx = sA + 4 * 128 * 128;
+    unsigned char* sB = sAx + 4096;                         // 4 x 6 KB SW128 + 1.5 KB k16 tile (1024-aligned)
+    __shared__ __align__(8) uint64_t bar_b, bar_mma;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc(&tmem_base, 64);
+    if (tid == 0) { mbar_init(&bar_b, 1); mbar_init(&bar_mma, 1); mbar_fence_init(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tmem_base;
+    constexpr uint32_t BBYTES = 4 * N * 128 + (N / 8) * 256;
+    if (tid == 0) { mbar_expect_tx(&bar_b, BBYTES); bulk_g2s(sB, Bimg, BBYTES, &bar_b); }
+    for (int k = 0; k < K; ++k) {
+        const __half h = __float2half_rn(A[tid * K + k]);
+        if (k < 256) *reinterpret_cast<__half*>(sA + sw128_offset(128, tid, k)) = h;
+        else *reinterpret_cast<__half*>(sAx + k16_offset(tid, k - 256)) = h;
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        mbar_wait(&bar_b, 0);
+        tc_fence_after();
+        constexpr uint32_t idesc = tc_idesc(128, N, 0);
+        for (int kb = 0; kb < 4; ++kb) {
+            const uint64_t ad = tc_smem_desc(smem_u32(sA + kb * 128 * 128));
+            const uint64_t bd = tc_smem_desc(smem_u32(sB + kb * N * 128));
+            for (int s = 0; s < 4; ++s) tc_mma(tb, ad + 2 * s, bd + 2 * s, idesc, (kb | s) != 0);
+        }
+        tc_mma(tb, tc_smem_desc_k16(smem_u32(sAx)), tc_smem_desc_k16(smem_u32(sB + 4 * N * 128)), idesc, 1u);
+        tc_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    for (int c = 0; c < N; c += 8) {
+        float v[8];
+        tmem_ld8(tb + ((uint32_t)(warp * 32) << 16) + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) D[tid * N + c + e] = v[e];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tb, 64);
+}
+
+extern "C" int toued_tc_gemm_mixed_test(const float* A, const float* B, void* scratch_img, float* D, void* stream) {
+    constexpr int N = 48, K = 272;
+    cudaStream_t st = (cudaStream_t)stream;
+    pack_b_mixed_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(B, (__half*)scratch_img, N, K);
+    TOUED_LAUNCH_CHECK();
+    const size_t smem = 4 * 128 * 128 + 4096 + 4 * N * 128 + 2048 + 1024;
+    TOUED_CUDA(cudaFuncSetAttribute(tc_gemm_mixed_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_gemm_mixed_test_kernel<<<1, 128, smem, st>>>(A, (const __half*)scratch_img, D);
+    TOUED_LAUNCH_CHECK();
+    return 0;
+}
