@@ -7,7 +7,7 @@
 //     (16 passes x [3 gates x 16 units = 48 rows][256 k] = 24 KB each) and streamed from L2 by a
 //     TMA-producer warp (cp.async.bulk + mbarrier, 2 stages);
 //   * the input projection x W_i + b_i rides in the same GEMM as a 17th K-step: a no-swizzle K = 16 block
-//     holding x_t (fp16, slot 7 = 1 for the bias); its MMA (N = 64) runs first and initialises the
+//     holding x_t twice (fp16, slot 7 = 1 for the bias) against the hi / lo fp16 split of W_i, b_i; its MMA (N = 64) runs first and initialises the
 //     accumulator columns (r | z | 0 | i_n), the recurrent MMAs (N = 48) accumulate onto (r | z | h_n)
 //     — i_n stays separate because r gates only the hidden part of the candidate;
 //   * one elected thread issues tcgen05.mma (M128 K16, 17 per pass) into a double-buffered TMEM
@@ -54,11 +54,14 @@ __global__ void pack_wi_fwd_kernel(const float* __restrict__ lpg, int X, __half*
     if (i >= FT_NPASS * FT_XN * 16) return;
     const int k = i & 15, row = (i >> 4) % FT_XN, p = i / (16 * FT_XN);
     const int blk = row >> 4, u = p * FT_PU + (row & 15);
+    // k in [8,16) holds the fp16 residual of slot k-8 (the x tile repeats x there): raw step / lifetime
+    // inputs reach a few hundred, so W_i is carried to ~22 bits
     float v = 0.0f;
     if (blk != 2) {
-        const int g = blk == 3 ? 2 : blk;
-        if (k < X) v = lpg[o.Wi + k * LPG_G + g * LPG_H + u];
-        else if (k == 7) v = lpg[o.bi + g * LPG_H + u];
+        const int g = blk == 3 ? 2 : blk, kk = k & 7;
+        if (kk < X) v = lpg[o.Wi + kk * LPG_G + g * LPG_H + u];
+        else if (kk == 7) v = lpg[o.bi + g * LPG_H + u];
+        if (k >= 8) v -= __half2float(__float2half_rn(v));
     }
     char* base = reinterpret_cast<char*>(img) + (size_t)p * FT_BSTAGE + FT_BH;
     *reinterpret_cast<__half*>(base + k16_offset(row, k)) = __float2half_rn(v);
@@ -106,7 +109,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
 
     for (int i = tid; i < LPG_H; i += FT_THREADS) { sbhn[i] = lpg[o.bhn + i]; swp[i] = lpg[o.w_pi + i]; }
     for (int i = tid; i < LPG_H * LPG_Y; i += FT_THREADS) sWy[i] = lpg[o.W_y + i];
-    // initial carry = 0 (both A buffers); x tiles zero (columns 8..15 stay zero), then x_{L-1} into tile 0
+    // initial carry = 0 (both A buffers); x tiles zero, then x_{L-1} into tile 0 (twice: W_i hi / lo parts)
     for (int i = tid; i < (2 * FT_ABUF + 2 * FT_AX) / 16; i += FT_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     if (tid < FT_M) {
@@ -120,6 +123,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
             pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
             pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
             *reinterpret_cast<uint4*>(sAx + k16_offset(tid, 0)) = pk;
+            *reinterpret_cast<uint4*>(sAx + k16_offset(tid, 8)) = pk;
         }
     }
     fence_proxy_async_smem();
@@ -202,6 +206,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                     pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
                 }
                 *reinterpret_cast<uint4*>(sAx + (cur ^ 1) * FT_AX + k16_offset(rl, 0)) = pk;
+                *reinterpret_cast<uint4*>(sAx + (cur ^ 1) * FT_AX + k16_offset(rl, 8)) = pk;
             }
             // mask for the NEXT processed step (t-1): its carry is zero where done[t-1]
             const bool zero_next = (t > 0) && done[((size_t)n_ag * L + (t - 1)) * W + w_ag];
