@@ -19,7 +19,7 @@
 constexpr int BT_M = 128;
 constexpr int BT_THREADS = 320;
 constexpr int BT_ACHUNK = BT_M * 128;            // 16 KB: [128 rows][64 bf16]
-constexpr int BT_ASTAGE = 5 * BT_ACHUNK;         // dG_r, dG_z, dG_hn, cz_hi, cz_lo
+constexpr int BT_ASTAGE = 6 * BT_ACHUNK;         // dG_r, dG_z, dG_hn, cz_hi, cz_lo, dG_an (store only)
 constexpr int BT_BCHUNK = LPG_H * 128;           // 32 KB: [256 units][64 c]
 constexpr int BT_NSB = 3;
 constexpr int BT_ICHUNK = 64 * 128;              // 8 KB identity
@@ -63,7 +63,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                        int R, int L, int W) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* sA = smem;                                   // 80 KB
+    unsigned char* sA = smem;                                   // 96 KB
     unsigned char* sB = sA + BT_ASTAGE;                         // 3 x 32 KB
     unsigned char* sI = sB + BT_NSB * BT_BCHUNK;                // 8 KB identity
     float* swp = reinterpret_cast<float*>(sI + BT_ICHUNK);      // [256]
@@ -79,7 +79,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
 
     if (tid == 0) {
         for (int s = 0; s < BT_NSB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        mbar_init(&a_full, 8); mbar_init(&a_empty, 1); mbar_init(&q_full, 1);
+        mbar_init(&a_full, 8); mbar_init(&a_empty, 2); mbar_init(&q_full, 1);
         mbar_fence_init();
     }
     if (warp == 9) tmem_alloc(&tmem_base_s, 512);
@@ -117,34 +117,53 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
         if (lane == 0) {
             constexpr uint32_t idesc256 = tc_idesc(BT_M, 256, 1), idesc64 = tc_idesc(BT_M, 64, 1);
             const uint32_t a_addr = smem_u32(sA), i_addr = smem_u32(sI);
-            uint32_t it = 0, ait = 0;
-            for (int t = 0; t + 1 < L; ++t) {
+            uint32_t it = 0;
+            const size_t Rp = ((size_t)R + 63) & ~(size_t)63;
+            const int nsub = ((size_t)row0 + 64 < Rp) ? 2 : 1;      // 64-token sub-tiles of this CTA inside the image
+            uint32_t ait = 0;
+            for (int t = 0; t < L; ++t) {
                 const uint32_t q_addr = tmem_base + (t & 1) * 256;
+                const bool mma = t + 1 < L;                          // the last step only stores its dG tiles
                 for (int ub = 0; ub < 4; ++ub, ++ait) {
                     mbar_wait(&a_full, ait & 1);
                     tc_fence_after();
-                    for (int g = 0; g < 3; ++g, ++it) {
-                        const int s = it % BT_NSB;
-                        mbar_wait(&b_full[s], (it / BT_NSB) & 1);
-                        tc_fence_after();
-                        const uint64_t ad = tc_smem_desc(a_addr + g * BT_ACHUNK);
-                        const uint64_t bd = tc_smem_desc(smem_u32(sB + s * BT_BCHUNK));
+                    if (mma) {
+                        for (int g = 0; g < 3; ++g, ++it) {
+                            const int s = it % BT_NSB;
+                            mbar_wait(&b_full[s], (it / BT_NSB) & 1);
+                            tc_fence_after();
+                            const uint64_t ad = tc_smem_desc(a_addr + g * BT_ACHUNK);
+                            const uint64_t bd = tc_smem_desc(smem_u32(sB + s * BT_BCHUNK));
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) tc_mma(q_addr, ad + 2 * ks, bd + 2 * ks, idesc256, (ub | g | ks) != 0);
-                        tc_commit(&b_empty[s]);
+                            for (int ks = 0; ks < 4; ++ks) tc_mma(q_addr, ad + 2 * ks, bd + 2 * ks, idesc256, (ub | g | ks) != 0);
+                            tc_commit(&b_empty[s]);
+                        }
+                        // z * dh_t (bf16 hi + lo) through the identity: accumulates onto columns [64 ub, 64 ub + 64)
+                        const uint64_t idd = tc_smem_desc(i_addr);
+#pragma unroll
+                        for (int c = 3; c < 5; ++c) {
+                            const uint64_t ad = tc_smem_desc(a_addr + c * BT_ACHUNK);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) tc_mma(q_addr + ub * 64, ad + 2 * ks, idd + 2 * ks, idesc64, 1u);
+                        }
                     }
-                    // z * dh_t (bf16 hi + lo) through the identity: accumulates onto columns [64 ub, 64 ub + 64)
-                    const uint64_t idd = tc_smem_desc(i_addr);
+                    tc_commit(&a_empty);                             // arrival 1 of 2: the MMAs have read the stage
+                    // dG tiles of this unit block -> token-tile image for the weight-gradient GEMM: the SW128
+                    // chunks in smem ARE the image's 8 KB sub-tiles, so they leave as full-line TMA bulk stores
+                    const size_t itok0 = (size_t)t * Rp + row0;
 #pragma unroll
-                    for (int c = 3; c < 5; ++c) {
-                        const uint64_t ad = tc_smem_desc(a_addr + c * BT_ACHUNK);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) tc_mma(q_addr + ub * 64, ad + 2 * ks, idd + 2 * ks, idesc64, 1u);
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t src = a_addr + (g == 3 ? 5 : g) * BT_ACHUNK;
+                        for (int sub = 0; sub < nsub; ++sub)
+                            bulk_s2g(dgimg + tile_img_offset(itok0 + sub * 64, 16, (g * 4 + ub) * 64), src + sub * 8192, 8192);
                     }
-                    tc_commit(&a_empty);
+                    bulk_commit();
+                    bulk_wait_read();
+                    mbar_arrive(&a_empty);                           // arrival 2 of 2: the stores have read the stage
                 }
-                tc_commit(&q_full);
+                if (mma) tc_commit(&q_full);
             }
+            bulk_wait_all();
         }
     } else {
         // ===================== epilogue / producer-of-A warps 0..7 =====================================
@@ -158,6 +177,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
         const size_t gs = (size_t)L * R32 * 32 * LPG_H;
         const size_t Rp = ((size_t)R + 63) & ~(size_t)63;
         uint32_t ait = 0;
+        const uint32_t sA_u32 = smem_u32(sA);
         // ---- software pipeline: the factor loads of the next 8-unit chunk and the head cotangents of the
         //      next timestep are issued one iteration ahead (across unit-block / timestep boundaries) ----
         struct FacLoads { uint4 fr, fz, fhn, fan, zz, hv; };
@@ -255,34 +275,22 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                             dx4 = fmaf(gr[e], w0.w, fmaf(gz[e], w1.x, fmaf(gan[e], w1.y, dx4)));
                         }
                     }
-                    const uint4 o_r = pack8bf(gr), o_z = pack8bf(gz), o_hn = pack8bf(ghn);
-                    if (rv) {      // token tile image for the weight-gradient kernels: 16 column groups
-                        const size_t itok = (size_t)t * Rp + row;
-                        const int cin = hf * 32 + c8 * 8;
-                        *reinterpret_cast<uint4*>(dgimg + tile_img_offset(itok, 16, (0 * 4 + ub) * 64 + cin)) = o_r;
-                        *reinterpret_cast<uint4*>(dgimg + tile_img_offset(itok, 16, (1 * 4 + ub) * 64 + cin)) = o_z;
-                        *reinterpret_cast<uint4*>(dgimg + tile_img_offset(itok, 16, (2 * 4 + ub) * 64 + cin)) = o_hn;
-                        *reinterpret_cast<uint4*>(dgimg + tile_img_offset(itok, 16, (3 * 4 + ub) * 64 + cin)) = pack8bf(gan);
-                    }
-                    if (t + 1 < L) {
-                        // the MMAs of the previous unit block must have consumed the A stage (they finished
-                        // long ago: this chunk's math alone takes longer than a block's MMAs)
-                        if (c8 == 0) mbar_wait(&a_empty, (ait & 1) ^ 1);
-                        const uint32_t so = sw128_offset(BT_M, rl, hf * 32 + c8 * 8);
-                        *reinterpret_cast<uint4*>(sA + 0 * BT_ACHUNK + so) = o_r;
-                        *reinterpret_cast<uint4*>(sA + 1 * BT_ACHUNK + so) = o_z;
-                        *reinterpret_cast<uint4*>(sA + 2 * BT_ACHUNK + so) = o_hn;
-                        *reinterpret_cast<uint4*>(sA + 3 * BT_ACHUNK + so) = pack8bf(czh);
-                        *reinterpret_cast<uint4*>(sA + 4 * BT_ACHUNK + so) = pack8bf(czl);
-                    }
+                    // the MMAs and the image stores of the previous unit block must have consumed the A stage
+                    // (they finished long ago: this chunk's math alone takes longer)
+                    if (c8 == 0 && ait > 0) mbar_wait(&a_empty, (ait & 1) ^ 1);
+                    const uint32_t so = sA_u32 + sw128_offset(BT_M, rl, hf * 32 + c8 * 8);
+                    st_shared_v4(so + 0 * BT_ACHUNK, pack8bf(gr));
+                    st_shared_v4(so + 1 * BT_ACHUNK, pack8bf(gz));
+                    st_shared_v4(so + 2 * BT_ACHUNK, pack8bf(ghn));
+                    st_shared_v4(so + 3 * BT_ACHUNK, pack8bf(czh));
+                    st_shared_v4(so + 4 * BT_ACHUNK, pack8bf(czl));
+                    st_shared_v4(so + 5 * BT_ACHUNK, pack8bf(gan));
                 }
-                if (t + 1 < L) {
-                    fence_proxy_async_smem();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&a_full);
-                    ++ait;
-                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full);
+                ++ait;
             }
             // d pyt / d pyt1: combine the two unit halves of the row
             if (hf == 1) { sdx[rl * 2] = dx3; sdx[rl * 2 + 1] = dx4; }
