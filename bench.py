@@ -222,6 +222,7 @@ def run_ours(a):
 
     # ---- timed region 2: end to end through the public API, host key in / metrics out each step ----
     barrier()
+    _lib.reset_counters(profile=False)
     t0 = time.perf_counter()
     d2h = 0
     for _ in range(a.steps):
@@ -246,7 +247,9 @@ def run_ours(a):
     value = total_env_steps / (ms_per_step * 1e-3)
     e2e_val = total_env_steps / (e2e_ms / a.steps * 1e-3)
     K, W, L = args.num_agent_updates, args.env_workers, args.train_rollout_len
-    h2d = AGENTS_PER_GPU * 8 * (K + 2)                               # per-agent rollout keys of one meta-step
+    # host->device bytes per step, counted where the package copies: the 8-byte step key, the lifetime mask
+    # and the records / init keys of the levels the sampler replaced
+    h2d = _lib.H2D_BYTES[0] / a.steps
 
     # ---- roofline of the dominant kernel (live CUDA-event times of the timed region) ----
     peaks = {}

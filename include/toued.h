@@ -189,6 +189,18 @@ int toued_init_tables(const uint32_t* keys, const uint8_t* mask, float* tables, 
 int toued_masked_reset(const void* levels, const uint8_t* mask, int32_t* state, int32_t* obs,
                        int32_t* step, int n_agents, int n_workers, int max_grid_size, void* stream);
 
+/* ---- key derivation on the device (jax 0.4.13 threefry2x32 split, bit-exact) ---------------------- */
+
+/* out u32[n_keys][count][2] = jax.random.split(keys_in[i], num)[offset : offset + count]
+ * (meta/train.py:38 ``jax.random.split(rng, num_agents)``, restricted to a rank's agents).          */
+int toued_key_split(const uint32_t* keys_in, int n_keys, int num, int offset, int count, uint32_t* out,
+                    void* stream);
+/* The ``rng, _rng = jax.random.split(rng)`` chain (lpg_agent.py:104-105, meta/train.py:40-42,109,
+ * agents.py:99-103): keys_out u32[chain_len][n_keys][2] = the _rng of every link, carry_out
+ * u32[n_keys][2] (or NULL) = the final rng.                                                          */
+int toued_key_chain(const uint32_t* keys_in, int n_keys, int chain_len, uint32_t* keys_out,
+                    uint32_t* carry_out, void* stream);
+
 /* ---- tensor-core (tcgen05 / TMEM) path -------------------------------------------------------- */
 
 /* Unit check of the tcgen05 building blocks: D f32[128][48] = A f32[128][256] * B f32[48][256]^T with

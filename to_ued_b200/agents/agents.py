@@ -77,11 +77,9 @@ def create_value_critic(rng, agent_params: AgentHyperparams, obs_shape, device="
 
 def eval_agent(rng, rollout_manager, env_params, actor_train_state, num_workers):
     """agents/agents.py:98-106, batched: rng uint32[N, 2] -> mean first-episode return f32[N]."""
-    rng = np.asarray(rng, np.uint32).reshape(-1, 2)
-    ks = prng.split(rng, 2)
-    rng, _rng = ks[:, 0, :], ks[:, 1, :]
-    env_obs, env_state = rollout_manager.batch_reset(_rng, env_params, num_workers)
-    ks = prng.split(rng, 2)
-    _, _, _, tot = rollout_manager.batch_rollout(ks[:, 1, :], actor_train_state, env_params, env_obs, env_state,
+    table = actor_train_state.params if hasattr(actor_train_state, "params") else actor_train_state
+    k_reset, k_roll = prng.chain_device(prng.to_device(rng, table.device), 2)     # agents.py:99-103
+    env_obs, env_state = rollout_manager.batch_reset(k_reset, env_params, num_workers)
+    _, _, _, tot = rollout_manager.batch_rollout(k_roll, actor_train_state, env_params, env_obs, env_state,
                                                  eval=True, want_trajectory=False)
     return tot.mean(dim=1)

@@ -147,12 +147,7 @@ def train_lpg_agent(rng, lpg_train_state, agent_state: AgentState, rollout_manag
     tape.actor[0].copy_(actor.params)
     tape.critic[0].copy_(critic.params)
     tape.scal_sum.zero_()
-    rng = np.asarray(rng, np.uint32).reshape(-1, 2)
-    keys = np.empty((K, N, 2), np.uint32)
-    for k in range(K):                                        # lpg_agent.py:104-105
-        ks = prng.split(rng, 2)
-        rng, keys[k] = ks[:, 0, :], ks[:, 1, :]
-    keys_d = torch.from_numpy(keys.view(np.int32)).to(dev, non_blocking=True)
+    keys_d = prng.chain_device(prng.to_device(rng, dev), K)   # lpg_agent.py:104-105, derived on the device
     s = _lib.stream_ptr()
     p = _lib.ptr
     lpg = lpg_train_state.params if hasattr(lpg_train_state, "params") else lpg_train_state

@@ -107,6 +107,7 @@ def pack_levels(params: EnvParams, lifetime=None, buffer_id=None) -> np.ndarray:
 
 def levels_to_device(rec: np.ndarray, device="cuda") -> torch.Tensor:
     t = torch.from_numpy(rec.view(np.uint8).reshape(len(rec), LEVEL_BYTES))
+    _lib.h2d(t)
     return t.pin_memory().to(device, non_blocking=True) if torch.cuda.is_available() else t
 
 

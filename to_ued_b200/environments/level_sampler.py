@@ -205,7 +205,7 @@ class LevelSampler:
         """Masked version of level_sampler.py:236-265: only terminated agents get new tables / envs."""
         dev = self.device
         D, W = self.obs_shape[0], self.env_workers
-        mask_d = torch.from_numpy(terminated.astype(np.uint8)).to(dev, non_blocking=True)
+        mask_d = _lib.h2d(torch.from_numpy(terminated.astype(np.uint8))).to(dev, non_blocking=True)
         new_levels = self._device_level(new_levels)
         ks = prng.split(agent_keys, 2)                       # worker_rng, agent_rng (level_sampler.py:275)
         ks2 = prng.split(ks[:, 1, :], 2)                     # actor_rng, critic_rng (agents.py:37)
@@ -244,7 +244,7 @@ class LevelSampler:
         a2c_agent, _ = train_a2c_agent(_rng, a2c_agent, self.rollout_manager, self.max_lifetime, self.a2c_hypers)
         ks = prng.split(rng, 2)
         lpg_rng, a2c_rng = ks[:, 0, :], ks[:, 1, :]
-        sel_d = torch.from_numpy(sel).to(self.device)
+        sel_d = _lib.h2d(torch.from_numpy(sel)).to(self.device)
         lpg_ret = eval_agent(lpg_rng, self.rollout_manager, a2c_agent.level.packed,
                              lpg_agent_state.actor_state.params[sel_d], self.env_workers)
         a2c_ret = eval_agent(a2c_rng, self.rollout_manager, a2c_agent.level.packed, a2c_agent.actor_state,

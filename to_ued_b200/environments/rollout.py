@@ -19,7 +19,7 @@ def _keys_to_device(rng, device):
     if isinstance(rng, torch.Tensor):
         return rng.to(device).contiguous().view(torch.int32)
     a = np.ascontiguousarray(np.asarray(rng, np.uint32)).view(np.int32)
-    return torch.from_numpy(a).to(device, non_blocking=True)
+    return _lib.h2d(torch.from_numpy(a)).to(device, non_blocking=True)
 
 
 class RolloutWrapper:

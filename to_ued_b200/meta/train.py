@@ -130,10 +130,9 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     p, s = _lib.ptr, _lib.stream_ptr()
 
     # ---- keys: split(rng, n_global)[local slice], then the per-agent chain of meta/train.py:40-110
-    rngs = prng.split(np.asarray(rng, np.uint32), n_global)[global_agent_offset:global_agent_offset + N]
-    ks = prng.split(rngs, 2); rngs, r_train = ks[:, 0, :], ks[:, 1, :]
-    ks = prng.split(rngs, 2); rngs, r_eval = ks[:, 0, :], ks[:, 1, :]
-    ks = prng.split(rngs, 2); r_evalagent = ks[:, 1, :]
+    #      derived on the device (csrc/prng.cu); the only host input of the step is the 8-byte key
+    rngs = prng.split_device(prng.to_device(rng, dev), n_global, global_agent_offset, N)[0]
+    r_train, r_eval, r_evalagent = prng.chain_device(rngs, 3)
 
     if N % num_mini_batches != 0:
         raise ValueError(f"local agents ({N}) must be divisible by num_mini_batches ({num_mini_batches})")
@@ -189,8 +188,7 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                                           lpg_hypers.agent_target_coeff, tape=tape)
             # ---- rollout the updated agent (meta/train.py:46-58) ----
             state = sub2.env_state.packed
-            keys_e = torch.from_numpy(np.ascontiguousarray(r_eval[sl]).view(np.int32)).to(dev, non_blocking=True)
-            _lib.call("toued_rollout", p(levels), p(keys_e), p(tape.actor[K]), None, p(state), p(tape.obs[K]),
+            _lib.call("toued_rollout", p(levels), p(r_eval[sl]), p(tape.actor[K]), None, p(state), p(tape.obs[K]),
                       p(tape.action[K]), p(tape.reward[K]), p(tape.done[K]), None, nb, W, L, D,
                       env.max_grid_size, env.max_n_objs, 0, s)
             _lib.call("toued_sort_tokens", p(tape.obs[K]), p(tape.sorted_tok[K]), nb, W, L, s)

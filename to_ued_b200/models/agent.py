@@ -7,6 +7,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from .. import _lib
 from ..util import prng
 
 TABLE_PAD = 8
@@ -31,12 +32,12 @@ def init_tables(keys, obs_dim: int, n_out: int, device="cuda", out=None, mask=No
     from .. import _lib
     keys = np.ascontiguousarray(np.asarray(keys, np.uint32).reshape(-1, 2))
     n = keys.shape[0]
-    kd = torch.from_numpy(keys.view(np.int32)).to(device, non_blocking=True)
+    kd = _lib.h2d(torch.from_numpy(keys.view(np.int32))).to(device, non_blocking=True)
     if out is None:
         out = torch.empty((n, obs_dim, TABLE_PAD), dtype=torch.float32, device=device)
     md = None
     if mask is not None:
-        md = mask if isinstance(mask, torch.Tensor) else torch.from_numpy(np.asarray(mask, np.uint8)).to(device, non_blocking=True)
+        md = mask if isinstance(mask, torch.Tensor) else _lib.h2d(torch.from_numpy(np.asarray(mask, np.uint8))).to(device, non_blocking=True)
     _lib.call("toued_init_tables", _lib.ptr(kd), _lib.ptr(md), _lib.ptr(out), n, obs_dim, n_out, _lib.stream_ptr())
     return out
 

@@ -104,3 +104,37 @@ def masked_topk(key, mask, k: int) -> np.ndarray:
     mant = (bits(key, (n,)) >> np.uint32(9)).astype(np.int64)
     rank_key = np.where(mask, -mant, np.int64(1) << 40)
     return np.argsort(rank_key, axis=-1, kind="stable")[..., :k].astype(np.int32)
+
+
+# ---- device-side derivation (csrc/prng.cu): same bits, no host threefry / H2D in front of a launch ----
+def to_device(key, device):
+    """uint32 key(s) (numpy [.., 2] or tensor) -> int32 cuda tensor [n, 2]."""
+    import torch
+    if isinstance(key, torch.Tensor):
+        return key.to(device).contiguous().view(torch.int32).reshape(-1, 2)
+    a = np.ascontiguousarray(np.asarray(key, np.uint32).reshape(-1, 2)).view(np.int32)
+    from .. import _lib
+    return _lib.h2d(torch.from_numpy(a)).to(device, non_blocking=True)
+
+
+def split_device(keys, num: int, offset: int = 0, count=None):
+    """jax.random.split(keys[i], num)[offset:offset+count] for every key: int32 cuda [n, count, 2]."""
+    import torch
+    from .. import _lib
+    count = num - offset if count is None else count
+    n = keys.shape[0]
+    out = torch.empty((n, count, 2), dtype=torch.int32, device=keys.device)
+    _lib.call("toued_key_split", _lib.ptr(keys), n, int(num), int(offset), int(count), _lib.ptr(out), _lib.stream_ptr())
+    return out
+
+
+def chain_device(keys, length: int, want_carry: bool = False):
+    """``rng, _rng = split(rng)`` repeated ``length`` times per key: int32 cuda [length, n, 2] of the _rng
+    (and the final rng [n, 2] when want_carry)."""
+    import torch
+    from .. import _lib
+    n = keys.shape[0]
+    out = torch.empty((length, n, 2), dtype=torch.int32, device=keys.device)
+    carry = torch.empty((n, 2), dtype=torch.int32, device=keys.device) if want_carry else None
+    _lib.call("toued_key_chain", _lib.ptr(keys), n, int(length), _lib.ptr(out), _lib.ptr(carry), _lib.stream_ptr())
+    return (out, carry) if want_carry else out
