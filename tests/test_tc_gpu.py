@@ -89,7 +89,7 @@ def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond):
                       p(tape.fac[0]), p(tape.hpimg[0]), p(tape.pi_hat[0]), p(tape.y_hat[0]), n, c.w, c.L, int(cond), s)
             R = n * c.w
             out[prec] = (tape.pi_hat[0].clone(), tape.y_hat[0].clone(), _from_rb32(tape.h16[0], c.L, R).float(),
-                         torch.stack([_from_rb32(tape.fac[0][i], c.L, R) for i in range(5)]).float())
+                         torch.stack([_from_rb32(tape.fac[0][i], c.L, R) for i in range(4)]).float())
             out["hpimg"] = tape.hpimg[0].clone()
         else:
             _lib.call("toued_gru_forward", p(tape.x[0]), p(tape.done[0]), p(lpg), p(tape.h[0]), p(tape.gates[0]),
@@ -98,8 +98,7 @@ def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond):
             h_ = tape.h[0]
             nd = (1 - tape.done[0].float()).permute(1, 0, 2).reshape(c.L, n * c.w, 1)     # [L][R][1]
             hp_ = torch.cat([h_[1:], torch.zeros_like(h_[:1])], 0) * nd                  # masked carry
-            fan = (1 - z_) * (1 - n_ * n_)
-            fac_ref = torch.stack([fan * hn_ * r_ * (1 - r_), (hp_ - n_) * z_ * (1 - z_), fan * r_, fan, z_])
+            fac_ref = torch.stack([r_, z_, n_, hn_])                 # the saved gate planes
             out[prec] = (tape.pi_hat[0].clone(), tape.y_hat[0].clone(), h_.clone(), fac_ref)
             out["hp_ref"] = hp_
     torch.cuda.synchronize()
@@ -108,7 +107,7 @@ def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond):
     e = rel_err(from_img.float().cpu().numpy(), out["hp_ref"].reshape(-1, 256).cpu().numpy())
     print(f"hp image: rel err {e:.2e}")
     assert e < 5e-3
-    names = ("pi_hat", "y_hat", "h", "factors")
+    names = ("pi_hat", "y_hat", "h", "gates")
     for nm, a, b in zip(names, out["tc"], out["fp32"]):
         e = rel_err(a.cpu().numpy(), b.cpu().numpy())
         print(f"tc vs fp32 {nm}: rel err {e:.2e}")

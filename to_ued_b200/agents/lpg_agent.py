@@ -68,7 +68,7 @@ class Tape:
             Rp = (R + 63) // 64 * 64
             R32 = (R + 31) // 32 * 32                         # RB32 layout pads rows to blocks of 32
             self.h16 = torch.empty((ka, L, R32, 256), dtype=f16, device=dev)
-            self.fac = torch.empty((ka, 5, L, R32, 256), dtype=f16, device=dev) if self.record else None
+            self.fac = torch.empty((ka, 4, L, R32, 256), dtype=f16, device=dev) if self.record else None
             # bf16 token-tile images (rows >= R of a partial 64-token block stay zero)
             self.hpimg = torch.zeros((ka, L * Rp * 256 * 2), dtype=torch.uint8, device=dev) if self.record else None
             self.ximg = torch.zeros((ka, L * Rp * 128), dtype=torch.uint8, device=dev) if self.record else None

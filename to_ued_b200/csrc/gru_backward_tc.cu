@@ -70,6 +70,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
     float* sWy = swp + LPG_H;                                   // [256][8]
     float* sWi = sWy + LPG_H * LPG_Y;                           // [256 units][8]: Wi rows 3, 4 x gates (r, z, n), 2 pad
     float* sdx = sWi + LPG_H * 8;                               // [128][2]
+    unsigned char* ssign = reinterpret_cast<unsigned char*>(sdx + BT_M * 2);   // [16 chunks][256 threads]: relu'(h_t) bits
     __shared__ __align__(8) uint64_t b_full[BT_NSB], b_empty[BT_NSB], a_full, a_empty, q_full;
     __shared__ uint32_t tmem_base_s;
 
@@ -180,19 +181,19 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
         const uint32_t sA_u32 = smem_u32(sA);
         // ---- software pipeline: the factor loads of the next 8-unit chunk and the head cotangents of the
         //      next timestep are issued one iteration ahead (across unit-block / timestep boundaries) ----
-        struct FacLoads { uint4 fr, fz, fhn, fan, zz, hv; };
+        struct FacLoads { uint4 r, z, n, hn, hx; };              // gates of step t, h of step t+1 (the carry h')
+        const size_t tstride = R32 * 32 * LPG_H;                 // RB32 elements per timestep
         auto issue_fac = [&](int t_, int ub_, int c8_) {
             FacLoads l;
             const size_t base = rb32_index((size_t)t_, R32, rsafe, ub_ * 64 + hf * 32 + c8_ * 8);
-            l.fr = *reinterpret_cast<const uint4*>(fac + base);
-            l.fz = *reinterpret_cast<const uint4*>(fac + gs + base);
-            l.fhn = *reinterpret_cast<const uint4*>(fac + 2 * gs + base);
-            l.fan = *reinterpret_cast<const uint4*>(fac + 3 * gs + base);
-            l.zz = *reinterpret_cast<const uint4*>(fac + 4 * gs + base);
-            l.hv = *reinterpret_cast<const uint4*>(h16 + base);
+            l.r = *reinterpret_cast<const uint4*>(fac + base);
+            l.z = *reinterpret_cast<const uint4*>(fac + gs + base);
+            l.n = *reinterpret_cast<const uint4*>(fac + 2 * gs + base);
+            l.hn = *reinterpret_cast<const uint4*>(fac + 3 * gs + base);
+            l.hx = t_ + 1 < L ? *reinterpret_cast<const uint4*>(h16 + base + tstride) : make_uint4(0u, 0u, 0u, 0u);
             return l;
         };
-        struct RowLoads { float4 y0, y1, d0, d1; float dpi; uint8_t dn; };
+        struct RowLoads { float4 y0, y1, d0, d1; float dpi; uint8_t dn, dn_hp; };
         auto issue_row = [&](int t_) {
             RowLoads r;
             const size_t tok_ = (size_t)t_ * R + rsafe;
@@ -201,8 +202,20 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
             r.y0 = q0[0]; r.y1 = q0[1]; r.d0 = q1[0]; r.d1 = q1[1];
             r.dpi = d_pi_hat[tok_];
             r.dn = t_ > 0 ? done[((size_t)n_ag * L + (t_ - 1)) * W + w_ag] : (uint8_t)1;
+            r.dn_hp = t_ + 1 < L ? done[((size_t)n_ag * L + t_) * W + w_ag] : (uint8_t)1;   // the cell at t consumed (1 - done_t) h_{t+1}
             return r;
         };
+        // relu'(h_0) bits of this thread's 16 chunks (later steps get theirs from the h' load one step earlier)
+        const int et = tid;                                      // 0..255 among the epilogue warps
+        for (int i = 0; i < 16; ++i) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(h16 + rb32_index(0, R32, rsafe, (i >> 2) * 64 + hf * 32 + (i & 3) * 8));
+            float v[8];
+            unpack8h(raw, v);
+            unsigned b = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) b |= (v[e] > 0.0f ? 1u : 0u) << e;
+            ssign[i * 256 + et] = (unsigned char)b;
+        }
         FacLoads nxt = issue_fac(0, 0, 0);
         RowLoads rnx = issue_row(0);
         for (int t = 0; t < L; ++t) {
@@ -228,6 +241,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
             }
             // carry mask: the cell at step t-1 consumed (1 - done_{t-1}) * h_t
             const float nd = (t > 0 && rv && !rc.dn) ? 1.0f : 0.0f;
+            const float nd_hp = rc.dn_hp ? 0.0f : 1.0f;
             if (t > 0) { mbar_wait(&q_full, (t - 1) & 1); tc_fence_after(); }
             const uint32_t p_addr = tmem_base + ((t - 1) & 1) * 256 + ((uint32_t)(q * 32) << 16);
             float dx3 = 0.f, dx4 = 0.f;
@@ -249,9 +263,17 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
 #pragma unroll
                         for (int e = 0; e < 8; ++e) carry[e] = 0.f;
                     }
-                    float fr[8], fz[8], fhn[8], fan[8], zz[8], hv[8];
-                    unpack8h(cur.fr, fr); unpack8h(cur.fz, fz); unpack8h(cur.fhn, fhn);
-                    unpack8h(cur.fan, fan); unpack8h(cur.zz, zz); unpack8h(cur.hv, hv);
+                    float gr_[8], zz[8], gn_[8], hn_[8], hx[8];
+                    unpack8h(cur.r, gr_); unpack8h(cur.z, zz); unpack8h(cur.n, gn_);
+                    unpack8h(cur.hn, hn_); unpack8h(cur.hx, hx);
+                    const int ci = ub * 4 + c8;
+                    const unsigned sg = ssign[ci * 256 + et];              // relu'(h_t)
+                    {
+                        unsigned b = 0;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) b |= (hx[e] > 0.0f ? 1u : 0u) << e;
+                        ssign[ci * 256 + et] = (unsigned char)b;          // relu'(h_{t+1}) for the next step
+                    }
                     float gr[8], gz[8], ghn[8], gan[8], czh[8], czl[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
@@ -262,10 +284,17 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                             float hd = dpi * swp[u];
                             hd = fmaf(dl[0], w0.x, hd); hd = fmaf(dl[1], w0.y, hd); hd = fmaf(dl[2], w0.z, hd); hd = fmaf(dl[3], w0.w, hd);
                             hd = fmaf(dl[4], w1.x, hd); hd = fmaf(dl[5], w1.y, hd); hd = fmaf(dl[6], w1.z, hd); hd = fmaf(dl[7], w1.w, hd);
-                            dh += hv[e] > 0.0f ? hd : 0.0f;
+                            dh += ((sg >> e) & 1u) ? hd : 0.0f;
                         }
                         if (!rv) dh = 0.0f;
-                        gr[e] = dh * fr[e]; gz[e] = dh * fz[e]; ghn[e] = dh * fhn[e]; gan[e] = dh * fan[e];
+                        // GRUCell backward factors from the saved gates (models/lpg.py:11-30):
+                        //   d a_n = dh (1-z)(1-n^2);  d(Whn h + bhn) = d a_n * r;  d a_r = d a_n * hn * r(1-r);
+                        //   d a_z = dh (h' - n) z(1-z)
+                        const float omz = 1.0f - zz[e];
+                        gan[e] = dh * omz * (1.0f - gn_[e] * gn_[e]);
+                        ghn[e] = gan[e] * gr_[e];
+                        gr[e] = ghn[e] * hn_[e] * (1.0f - gr_[e]);
+                        gz[e] = dh * (nd_hp * hx[e] - gn_[e]) * zz[e] * omz;
                         const float cz = dh * zz[e];
                         czh[e] = __bfloat162float(__float2bfloat16_rn(cz));
                         czl[e] = cz - czh[e];
@@ -305,7 +334,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
 }
 
 static size_t gru_bwd_tc_smem() {
-    return BT_ASTAGE + BT_NSB * BT_BCHUNK + BT_ICHUNK + sizeof(float) * (LPG_H + LPG_H * LPG_Y + LPG_H * 8 + BT_M * 2) + 1024;
+    return BT_ASTAGE + BT_NSB * BT_BCHUNK + BT_ICHUNK + sizeof(float) * (LPG_H + LPG_H * LPG_Y + LPG_H * 8 + BT_M * 2) + 16 * 256 + 1024;
 }
 
 extern "C" int toued_gru_backward_tc(const uint8_t* done, const float* lpg_params, const void* whb_img,

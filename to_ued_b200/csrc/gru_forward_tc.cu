@@ -237,21 +237,15 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                 float hp[8];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hp2[e]); hp[2 * e] = f.x; hp[2 * e + 1] = f.y; }
-                float hv[8], fr[8], fz[8], fhn[8], fan[8], zz[8];
+                float hv[8], rr[8], zz[8], nn[8], hn[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int u = u0 + e;
-                    const float gr = ar[e], gz = az[e], gn = ai[e];      // input projection + bias already inside
-                    const float rr = sigmoid_fast(gr);
-                    zz[e] = sigmoid_fast(gz);
-                    const float hn = an[e] + sbhn[u];
-                    const float nn = tanh_fast(gn + rr * hn);
-                    hv[e] = (1.0f - zz[e]) * nn + zz[e] * hp[e];
-                    // reverse-pass factors: d(pre-activation) = dh * factor   (lpg.py GRUCell backward)
-                    fan[e] = (1.0f - zz[e]) * (1.0f - nn * nn);          // dan = dh * fan
-                    fhn[e] = fan[e] * rr;                                 // d(Whn h + bhn) = dan * r
-                    fr[e] = fan[e] * hn * rr * (1.0f - rr);               // dar
-                    fz[e] = (hp[e] - nn) * zz[e] * (1.0f - zz[e]);        // daz
+                    rr[e] = sigmoid_fast(ar[e]);                          // input projection + bias already inside
+                    zz[e] = sigmoid_fast(az[e]);
+                    hn[e] = an[e] + sbhn[u];
+                    nn[e] = tanh_fast(ai[e] + rr[e] * hn[e]);
+                    hv[e] = (1.0f - zz[e]) * nn[e] + zz[e] * hp[e];
                     const float y = fmaxf(hv[e], 0.0f);
                     head[0] = fmaf(y, swp[u], head[0]);
                     {
@@ -282,11 +276,11 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                     const size_t so = tokbase + ((size_t)(u0 >> 3) << 8);          // RB32: chunk stride 256 elements
                     *reinterpret_cast<uint4*>(h16 + so) = hpk;
                     if (fac) {
-                        *reinterpret_cast<uint4*>(fac + so) = pack8(fr);
-                        *reinterpret_cast<uint4*>(fac + gs + so) = pack8(fz);
-                        *reinterpret_cast<uint4*>(fac + 2 * gs + so) = pack8(fhn);
-                        *reinterpret_cast<uint4*>(fac + 3 * gs + so) = pack8(fan);
-                        *reinterpret_cast<uint4*>(fac + 4 * gs + so) = pack8(zz);
+                        // the reverse pass rebuilds its factors from the gates (and h' from h16 of step t+1)
+                        *reinterpret_cast<uint4*>(fac + so) = pack8(rr);
+                        *reinterpret_cast<uint4*>(fac + gs + so) = pack8(zz);
+                        *reinterpret_cast<uint4*>(fac + 2 * gs + so) = pack8(nn);
+                        *reinterpret_cast<uint4*>(fac + 3 * gs + so) = pack8(hn);
                     }
                     if (hpimg) {
                         // h' consumed at step t-1 (= masked h_t), bf16 token-tile image for the weight-gradient GEMM
