@@ -58,6 +58,14 @@ __device__ __forceinline__ uint64_t tc_smem_desc_mn(uint32_t smem_addr, uint32_t
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | (64ull << 32) |
            (1ull << 46) | (2ull << 61);
 }
+// MN-major operand WITHOUT swizzle: 8 (k) x 16-byte (8 MN-elements) core matrices of 128 contiguous bytes;
+// in this mode (unlike the swizzled MN-major modes) `lbo_bytes` = distance to the next 8 k-rows and
+// `sbo_bytes` = distance to the next 8 MN-elements.  The RB32 activation layout [chunk][32 rows][8 units]
+// is exactly this with lbo = 128, sbo = 512 (k = rows).
+__device__ __forceinline__ uint64_t tc_smem_desc_mn_plain(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
 // instruction descriptor with both operands MN-major (weight-gradient GEMMs)
 __host__ __device__ constexpr uint32_t tc_idesc_mn(int M, int N, int fmt) {
     return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | (1u << 15) | (1u << 16) |

@@ -104,45 +104,62 @@ wgrad_wh_tc_kernel(const unsigned char* __restrict__ hpimg, const unsigned char*
             // Always accumulates: the head-gradient kernel has initialised this split's small-partial area.
             if (warp == 0) {
                 float* out = small_partial + (size_t)split * SMT_TOTAL;
-                for (int c = 0; c < 512; c += 8) {
-                    float v[8];
-                    if (nblk > 0) { tmem_ld8(tmem_base + c, v); tmem_ld_wait(); }
-                    else {
+                auto dst_of = [&](int cc) {
+                    if (ct == 0) return SMT_WI + lane * LPG_G + cc;                            // dar, daz columns
+                    if (cc >= 256) return SMT_WI + lane * LPG_G + 512 + (cc - 256);           // dan columns
+                    return lane == 7 ? SMT_BHN + cc : -1;                                     // sum of dhn
+                };
+                for (int c = 0; c < 512; c += 32) {          // 32 columns per round: loads first, then the stores
+                    float v[4][8], o[4][8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                    for (int i = 0; i < 4; ++i) {
+                        if (nblk > 0) tmem_ld8(tmem_base + c + 8 * i, v[i]);
+                        else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+                        }
                     }
+                    if (nblk > 0) tmem_ld_wait();
                     if (lane < 8) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int cc = c + e;
-                            int dst = -1;
-                            if (ct == 0) dst = SMT_WI + lane * LPG_G + cc;                       // dar, daz columns
-                            else if (cc >= 256) dst = SMT_WI + lane * LPG_G + 512 + (cc - 256);  // dan columns
-                            else if (lane == 7) dst = SMT_BHN + cc;                              // sum of dhn
-                            if (dst >= 0) out[dst] += v[e];
-                        }
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) { const int d = dst_of(c + 8 * i + e); o[i][e] = d >= 0 ? out[d] : 0.0f; }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) { const int d = dst_of(c + 8 * i + e); if (d >= 0) out[d] = o[i][e] + v[i][e]; }
                     }
                 }
             }
         } else {
         const int j = jt * 128 + warp * 32 + lane;
         float* out = partial + (size_t)split * LPG_H * LPG_G + (size_t)j * LPG_G + ct * 384;
-        for (int c = 0; c < 384; c += 8) {
-            float v[8];
-            if (nblk > 0) {
-                tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + c, v);
-                tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = 0.f;
-            }
+        // 64 columns per round: the previous partials are fetched with 16 independent loads in flight
+        // (one dependent load -> add -> store round trip per 8 columns would serialise 48 DRAM latencies)
+        for (int c = 0; c < 384; c += 64) {
+            float4 pre[16];
             float4* p = reinterpret_cast<float4*>(out + c);
             if (accumulate) {
-                const float4 p0 = p[0], p1 = p[1];
-                v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pre[i] = p[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            p[0] = make_float4(v[0], v[1], v[2], v[3]);
-            p[1] = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float v[8];
+                if (nblk > 0) {
+                    tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + c + 8 * i, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                }
+                p[2 * i] = make_float4(v[0] + pre[2 * i].x, v[1] + pre[2 * i].y, v[2] + pre[2 * i].z, v[3] + pre[2 * i].w);
+                p[2 * i + 1] = make_float4(v[4] + pre[2 * i + 1].x, v[5] + pre[2 * i + 1].y, v[6] + pre[2 * i + 1].z, v[7] + pre[2 * i + 1].w);
+            }
         }
         }
     }
@@ -156,15 +173,48 @@ wgrad_wh_tc_kernel(const unsigned char* __restrict__ hpimg, const unsigned char*
 // coalesced 512-byte line; each lane keeps 8 x 9 accumulators over all the row blocks of its split and the
 // 32 rows are combined once at the end by a fixed shuffle tree (deterministic).
 constexpr int HT_SPLITS = 148;
+// Every lane only ever needs its own row's data, so each lane runs a private
+// HT_DEPTH-deep cp.async ring (no barriers, no producer warp): 16 B of h16, 32 B of dl and 4 B of d_pi_hat
+// per row block in flight HT_DEPTH blocks ahead.
+constexpr int HT_DEPTH = 6;
+constexpr int HT_SLOT = 64;                  // bytes per lane per stage: h16 [0,16) | dl [16,48) | d_pi_hat [48,52)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
 __global__ void __launch_bounds__(256)
-wgrad_heads_tc_kernel(const __half* __restrict__ h16, const float* __restrict__ d_pi_hat, const float* __restrict__ dl,
-                      float* __restrict__ partial, int R, int L, int blocks_per_split, int accumulate) {
+wgrad_heads_stream_kernel(const __half* __restrict__ h16, const float* __restrict__ d_pi_hat, const float* __restrict__ dl,
+                          float* __restrict__ partial, int R, int L, int blocks_per_split, int accumulate) {
+    extern __shared__ __align__(128) unsigned char hsm[];     // [HT_DEPTH][256 threads][HT_SLOT]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = blockIdx.x * 8 + warp;            // 0..31
     const int split = blockIdx.y;
     const int R32 = (R + 31) >> 5;
-    const int nrb = L * R32;                             // (t, row block) pairs
+    const int nrb = L * R32;
     const int b0 = split * blocks_per_split, b1 = min(nrb, b0 + blocks_per_split);
+    const uint32_t slot0 = smem_u32(hsm) + threadIdx.x * HT_SLOT;
+    // producer-side cursor (block ib = (it, irb), ring stage istage); all counters advance incrementally:
+    // divisions in this loop cost more than its 72 FMAs
+    int ib = b0, it = b0 / R32, irb = b0 % R32, istage = 0;
+    auto issue = [&]() {
+        if (ib < b1) {
+            const int row = irb * 32 + lane;
+            if (row < R) {
+                const size_t tok = (size_t)it * R + row;
+                const uint32_t d = slot0 + istage * (256 * HT_SLOT);
+                cp_async16(d, h16 + (((size_t)ib * 32 + chunk) << 8) + (lane << 3));
+                cp_async16(d + 16, dl + tok * 8);
+                cp_async16(d + 32, dl + tok * 8 + 4);
+                cp_async4(d + 48, d_pi_hat + tok);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        ++ib;
+        if (++irb == R32) { irb = 0; ++it; }
+        if (++istage == HT_DEPTH) istage = 0;
+    };
     float acc[8][9], hb[9];
 #pragma unroll
     for (int e = 0; e < 8; ++e)
@@ -172,14 +222,20 @@ wgrad_heads_tc_kernel(const __half* __restrict__ h16, const float* __restrict__ 
         for (int i = 0; i < 9; ++i) acc[e][i] = 0.f;
 #pragma unroll
     for (int i = 0; i < 9; ++i) hb[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < HT_DEPTH - 1; ++i) issue();
+    int crb = b0 % R32, cstage = 0;
     for (int b = b0; b < b1; ++b) {
-        const int t = b / R32, rb = b % R32;
-        const int row = rb * 32 + lane;
+        issue();
+        asm volatile("cp.async.wait_group %0;" ::"n"(HT_DEPTH - 1) : "memory");
+        const int row = crb * 32 + lane;
+        const unsigned char* st = hsm + cstage * (256 * HT_SLOT) + threadIdx.x * HT_SLOT;
+        if (++crb == R32) crb = 0;
+        if (++cstage == HT_DEPTH) cstage = 0;
         if (row >= R) continue;
-        const size_t tok = (size_t)t * R + row;
-        const uint4 raw = *reinterpret_cast<const uint4*>(h16 + (((size_t)b * 32 + chunk) << 8) + (lane << 3));
-        const float4 d0 = *reinterpret_cast<const float4*>(dl + tok * 8), d1 = *reinterpret_cast<const float4*>(dl + tok * 8 + 4);
-        const float dv[9] = {d_pi_hat[tok], d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        const uint4 raw = *reinterpret_cast<const uint4*>(st);
+        const float4 d0 = *reinterpret_cast<const float4*>(st + 16), d1 = *reinterpret_cast<const float4*>(st + 32);
+        const float dv[9] = {*reinterpret_cast<const float*>(st + 48), d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
         const __half2* hh = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
@@ -195,6 +251,8 @@ wgrad_heads_tc_kernel(const __half* __restrict__ h16, const float* __restrict__ 
     }
     float* out = partial + (size_t)split * SMT_TOTAL;
     auto put = [&](int idx, float v) { out[idx] = accumulate ? out[idx] + v : v; };
+    // butterfly sums leave the total in every lane; lane (j mod 32) owns value j, so the read-modify-writes
+    // of a warp go out in parallel instead of 72 dependent round trips from lane 0
 #pragma unroll
     for (int e = 0; e < 8; ++e)
 #pragma unroll
@@ -202,7 +260,7 @@ wgrad_heads_tc_kernel(const __half* __restrict__ h16, const float* __restrict__ 
             float v = acc[e][i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) { if (i == 0) put(SMT_WPI + chunk * 8 + e, v); else put(SMT_WY + (chunk * 8 + e) * 8 + (i - 1), v); }
+            if (lane == ((e * 9 + i) & 31)) { if (i == 0) put(SMT_WPI + chunk * 8 + e, v); else put(SMT_WY + (chunk * 8 + e) * 8 + (i - 1), v); }
         }
     if (chunk == 0) {
 #pragma unroll
@@ -210,12 +268,185 @@ wgrad_heads_tc_kernel(const __half* __restrict__ h16, const float* __restrict__ 
             float v = hb[i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) put(SMT_BPI + i, v);
+            if (lane == 16 + i) put(SMT_BPI + i, v);
         }
     }
     if (!accumulate) {                    // the x-tile CTAs of the GEMM kernel add into the input-side area
         for (int i = blockIdx.x * 256 + threadIdx.x; i < SMT_WPI; i += 4 * 256) out[i] = 0.0f;
     }
+}
+
+// ---- head gradients on the tensor cores (R % 32 == 0) ---------------------------------------------------
+// dw_pi / dW_y = relu(h)^T [256 units x tokens] . [d pi_hat | dl] [tokens x 9]: a GEMM contracted over tokens.
+// A 32-row block of the RB32 activation layout (16 KB contiguous) is, as it lies in memory, an MN-major
+// no-swizzle tcgen05 operand (k = rows).  Per block: TMA bulk copy -> four warps apply relu and convert
+// fp16 -> bf16 in place and build the B operand from the fp32 cotangents as a bf16 hi + lo pair (N = 32:
+// columns 0..15 hi, 16..31 lo, so the cotangents keep ~16 mantissa bits) -> 4 MMAs (M128 N32 K16).
+constexpr int HM_NS = 4;
+constexpr int HM_A = 16384, HM_RAW = 1024 + 128, HM_B = 2048;
+constexpr int HM_STAGE = HM_A + HM_RAW + HM_B;            // 19584 B (multiple of 128)
+constexpr int HM_THREADS = 192;
+__global__ void __launch_bounds__(HM_THREADS, 1)
+wgrad_heads_mma_kernel(const __half* __restrict__ h16, const float* __restrict__ d_pi_hat, const float* __restrict__ dl,
+                       float* __restrict__ partial, int R, int L, int blocks_per_split, int accumulate) {
+    extern __shared__ __align__(1024) unsigned char hm_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(hm_raw) + 127) & ~uintptr_t(127));
+    __shared__ __align__(8) uint64_t full[HM_NS], ready[HM_NS], empty[HM_NS], done_bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int split = blockIdx.x;
+    const int R32 = R >> 5;
+    const int nrb = L * R32;
+    const int b0 = split * blocks_per_split, b1 = min(nrb, b0 + blocks_per_split);
+    const int nblk = max(0, b1 - b0);
+    if (tid == 0) {
+        for (int s = 0; s < HM_NS; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
+        mbar_init(&done_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 5) tmem_alloc(&tmem_base_s, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            int t = b0 / R32, rb = b0 % R32;
+            for (int i = 0; i < nblk; ++i) {
+                const int s = i % HM_NS;
+                mbar_wait(&empty[s], ((i / HM_NS) & 1) ^ 1);
+                unsigned char* st = smem + s * HM_STAGE;
+                const size_t tok0 = (size_t)t * R + (size_t)rb * 32;
+                mbar_expect_tx(&full[s], HM_A + HM_RAW);
+                bulk_g2s(st, h16 + ((size_t)(b0 + i) << 13), HM_A, &full[s]);
+                bulk_g2s(st + HM_A, dl + tok0 * 8, 1024, &full[s]);
+                bulk_g2s(st + HM_A + 1024, d_pi_hat + tok0, 128, &full[s]);
+                if (++rb == R32) { rb = 0; ++t; }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            // (kind::f16 needs A and B in the same 16-bit format on this part: fp16 x bf16 traps, so relu(h) is
+            //  converted to bf16 by the transform warps)
+            constexpr uint32_t idesc = tc_idesc_mn(128, 32, 1);
+            for (int i = 0; i < nblk; ++i) {
+                const int s = i % HM_NS;
+                mbar_wait(&ready[s], (i / HM_NS) & 1);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(smem + s * HM_STAGE), bb = a0 + HM_A + HM_RAW;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const uint64_t bd = tc_smem_desc_mn_plain(bb + ks * 256, 128, 512);
+#pragma unroll
+                    for (int mh = 0; mh < 2; ++mh)
+                        tc_mma(tmem_base + mh * 32, tc_smem_desc_mn_plain(a0 + mh * 8192 + ks * 256, 128, 512), bd, idesc,
+                               (i | ks) != 0);
+                }
+                tc_commit(&empty[s]);
+            }
+            tc_commit(&done_bar);
+        }
+    } else {
+        // ---- transform warps (0..3), later the epilogue ----
+        float hb[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) hb[i] = 0.f;
+        for (int i = 0; i < nblk; ++i) {
+            const int s = i % HM_NS;
+            mbar_wait(&full[s], (i / HM_NS) & 1);
+            unsigned char* st = smem + s * HM_STAGE;
+            // relu + fp16 -> bf16 in place: 1024 16-byte groups, 8 per thread (consecutive threads, consecutive groups)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                uint4* pp = reinterpret_cast<uint4*>(st) + q * 128 + tid;
+                const uint4 raw = *pp;
+                const __half2* hh = reinterpret_cast<const __half2*>(&raw);
+                uint4 o;
+                uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(hh[e]);
+                    const __nv_bfloat162 b = __floats2bfloat162_rn(fmaxf(f.x, 0.0f), fmaxf(f.y, 0.0f));
+                    ow[e] = *reinterpret_cast<const uint32_t*>(&b);
+                }
+                *pp = o;
+            }
+            if (warp == 0) {
+                // B operand for row `lane`: [n-group g][k = row][8] bf16; groups 0,1 = hi of (d pi_hat, dl[0..7], 0..),
+                // groups 2,3 = lo
+                const float4 d0 = *reinterpret_cast<const float4*>(st + HM_A + lane * 32), d1 = *reinterpret_cast<const float4*>(st + HM_A + lane * 32 + 16);
+                const float dv[9] = {*reinterpret_cast<const float*>(st + HM_A + 1024 + lane * 4), d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                float hi[9], lo[9];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) {
+                    hi[j] = __bfloat162float(__float2bfloat16_rn(dv[j]));
+                    lo[j] = dv[j] - hi[j];
+                    hb[j] += dv[j];
+                }
+                auto pk = [](float a, float b) { const __nv_bfloat162 v = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&v); };
+                unsigned char* bp = st + HM_A + HM_RAW + lane * 16;
+                *reinterpret_cast<uint4*>(bp) = make_uint4(pk(hi[0], hi[1]), pk(hi[2], hi[3]), pk(hi[4], hi[5]), pk(hi[6], hi[7]));
+                *reinterpret_cast<uint4*>(bp + 512) = make_uint4(pk(hi[8], 0.f), 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(bp + 1024) = make_uint4(pk(lo[0], lo[1]), pk(lo[2], lo[3]), pk(lo[4], lo[5]), pk(lo[6], lo[7]));
+                *reinterpret_cast<uint4*>(bp + 1536) = make_uint4(pk(lo[8], 0.f), 0u, 0u, 0u);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready[s]);
+        }
+        // ---- epilogue: TMEM lane = unit within the 128-unit half ----
+        mbar_wait(&done_bar, 0);
+        tc_fence_after();
+        float* out = partial + (size_t)split * SMT_TOTAL;
+#pragma unroll
+        for (int mh = 0; mh < 2; ++mh) {
+            const int u = mh * 128 + warp * 32 + lane;
+            float v[4][8];
+            if (nblk > 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + mh * 32 + 8 * q, v[q]);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[q][e] = 0.f;
+            }
+            float g[9];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = v[0][j] + v[2][j];
+            g[8] = v[1][0] + v[3][0];
+            // (SMT_TOTAL is odd: no vector accesses into a split's area)
+            float* wy = out + SMT_WY + u * 8;
+            float prev[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) prev[j] = 0.f;
+            if (accumulate) {
+                prev[0] = out[SMT_WPI + u];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) prev[1 + j] = wy[j];
+            }
+            out[SMT_WPI + u] = prev[0] + g[0];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wy[j] = prev[1 + j] + g[1 + j];
+        }
+        if (warp == 0) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                float v = hb[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == i) out[SMT_BPI + i] = accumulate ? out[SMT_BPI + i] + v : v;
+            }
+        }
+        if (!accumulate) {                // the x-tile CTAs of the GEMM kernel add into the input-side area
+            for (int i = tid; i < SMT_WPI; i += 128) out[i] = 0.0f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 64);
 }
 
 constexpr int WT_SPLITS = 24;              // 6 tile types x 24 = 144 CTAs
@@ -235,7 +466,17 @@ extern "C" int toued_lpg_wgrad_tc(const void* hpimg, const void* dgimg, const vo
     // head gradients first: also zero-initialises the input-side area the GEMM's x tiles accumulate into
     const int nrb = L * ((R + 31) / 32);
     const int rbps = (nrb + HT_SPLITS - 1) / HT_SPLITS;
-    wgrad_heads_tc_kernel<<<dim3(4, HT_SPLITS), 256, 0, st>>>((const __half*)h16, d_pi_hat, dl, small_partials, R, L, rbps, accumulate);
+    if (R % 32 == 0) {
+        constexpr int msmem = HM_NS * HM_STAGE + 128;
+        TOUED_CUDA(cudaFuncSetAttribute(wgrad_heads_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
+        wgrad_heads_mma_kernel<<<HT_SPLITS, HM_THREADS, msmem, st>>>((const __half*)h16, d_pi_hat, dl, small_partials,
+                                                                    R, L, rbps, accumulate);
+    } else {
+        constexpr int hsmem = HT_DEPTH * 256 * HT_SLOT;
+        TOUED_CUDA(cudaFuncSetAttribute(wgrad_heads_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem));
+        wgrad_heads_stream_kernel<<<dim3(4, HT_SPLITS), 256, hsmem, st>>>((const __half*)h16, d_pi_hat, dl, small_partials,
+                                                                         R, L, rbps, accumulate);
+    }
     TOUED_LAUNCH_CHECK();
     const size_t smem = WT_NS * WT_STAGE + 1024;
     TOUED_CUDA(cudaFuncSetAttribute(wgrad_wh_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
