@@ -62,7 +62,9 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                        unsigned char* __restrict__ dgimg, float* __restrict__ dl_out, float* __restrict__ dx,
                        int R, int L, int W) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // (offset arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared
+    //  address space and emits LDS / STS instead of generic LD / ST)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* sA = smem;                                   // 96 KB
     unsigned char* sB = sA + BT_ASTAGE;                         // 3 x 32 KB
     unsigned char* sI = sB + BT_NSB * BT_BCHUNK;                // 8 KB identity

@@ -34,7 +34,7 @@ constexpr int FT_BSTAGE = FT_BH + FT_BX;           // 26624 B per pass image (mu
 constexpr int FT_AX = (FT_M / 8) * 256;            // 4096 B: x tile of the A operand
 constexpr int FT_ABUF = FT_KB * FT_M * 128;        // 65536 B
 constexpr int FT_NS = 2;                  // B stages
-constexpr int FT_THREADS = 320;           // 8 epilogue warps + producer warp + MMA warp
+constexpr int FT_THREADS = 576;           // 2 sets of 8 epilogue warps (even / odd passes) + producer warp + MMA warp
 
 // Wh[k][c] (fp32, c = g*256 + unit) -> fp16 pass images: image[p][kb][row = g*16 + u][128 B swizzled]
 __global__ void pack_wh_fwd_kernel(const float* __restrict__ Wh, __half* __restrict__ img) {
@@ -84,15 +84,16 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                       __half* __restrict__ h16, __half* __restrict__ fac, unsigned char* __restrict__ hpimg,
                       float* __restrict__ pi_hat, float* __restrict__ y_hat, int R, int L, int W) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // (offset arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared
+    //  address space and emits LDS / STS instead of generic LD / ST)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* sA = smem;                                   // 2 x 64 KB   h' (SW128 K-blocks)
     unsigned char* sAx = sA + 2 * FT_ABUF;                      // 2 x 4 KB    x tile (no-swizzle K = 16 block)
     unsigned char* sB = sAx + 2 * FT_AX;                        // FT_NS x 26 KB
-    float* sbhn = reinterpret_cast<float*>(sB + FT_NS * FT_BSTAGE);   // [256]
-    float* swp = sbhn + LPG_H;                                  // [256]
-    float* sWy = swp + LPG_H;                                   // [256][8]
-    float* shead = sWy + LPG_H * LPG_Y;                         // [128][9] partial heads of the hf=1 half
+    unsigned char* sHB = sB + FT_NS * FT_BSTAGE;                // 16 x 1 KB   head weights [w_pi | W_y] as fp16 hi / lo, per pass
+    float* sbhn = reinterpret_cast<float*>(sHB + FT_NPASS * 1024);    // [256]
     __shared__ __align__(8) uint64_t b_full[FT_NS], b_empty[FT_NS], acc_full[2], acc_empty[2], a_ready;
+    __shared__ __align__(8) uint64_t stage_full[2], stage_empty[2], heads_full[2];
     __shared__ uint32_t tmem_base_s;
 
     const LpgOffsets o = lpg_offsets(X);
@@ -102,13 +103,21 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
     if (tid == 0) {
         for (int s = 0; s < FT_NS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
-        mbar_init(&a_ready, 8);
+        mbar_init(&a_ready, 16);
+        for (int a = 0; a < 2; ++a) { mbar_init(&stage_full[a], 8); mbar_init(&stage_empty[a], 1); mbar_init(&heads_full[a], 1); }
         mbar_fence_init();
     }
-    if (warp == 9) tmem_alloc(&tmem_base_s, 128);
+    if (warp == 17) tmem_alloc(&tmem_base_s, 256);     // 2 x 64 gate accumulators + 2 x 32 head accumulators + 2 x 8 relu(h) tiles
 
-    for (int i = tid; i < LPG_H; i += FT_THREADS) { sbhn[i] = lpg[o.bhn + i]; swp[i] = lpg[o.w_pi + i]; }
-    for (int i = tid; i < LPG_H * LPG_Y; i += FT_THREADS) sWy[i] = lpg[o.W_y + i];
+    for (int i = tid; i < LPG_H; i += FT_THREADS) sbhn[i] = lpg[o.bhn + i];
+    // head weights as the B operand of the heads MMA: per pass a [32 n][16 k] no-swizzle block; n < 16: fp16 of
+    // (w_pi, W_y[.,0..7], 0..), n >= 16: the fp16 residual, so the heads keep ~22 weight bits
+    for (int i = tid; i < FT_NPASS * 32 * 16; i += FT_THREADS) {
+        const int p = i >> 9, n = (i >> 4) & 31, k = i & 15, u = p * FT_PU + k, nn = n & 15;
+        const float w = nn == 0 ? lpg[o.w_pi + u] : (nn < 1 + LPG_Y ? lpg[o.W_y + u * LPG_Y + nn - 1] : 0.0f);
+        const float hi = __half2float(__float2half_rn(w));
+        *reinterpret_cast<__half*>(sHB + p * 1024 + k16_offset(n, k)) = __float2half_rn(n < 16 ? hi : w - hi);
+    }
     // initial carry = 0 (both A buffers); x tiles zero, then x_{L-1} into tile 0 (twice: W_i hi / lo parts)
     for (int i = tid; i < (2 * FT_ABUF + 2 * FT_AX) / 16; i += FT_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
@@ -132,7 +141,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp == 8) {
+    if (warp == 16) {
         // ===================== TMA producer: stream the 16 pass images per step =====================
         if (lane == 0) {
             uint32_t it = 0;
@@ -146,11 +155,24 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 17) {
         // ===================== MMA issuer ==========================================================
         if (lane == 0) {
-            constexpr uint32_t idesc = tc_idesc(FT_M, FT_PN, 0), idesc_x = tc_idesc(FT_M, FT_XN, 0);
-            uint32_t it = 0;
+            constexpr uint32_t idesc = tc_idesc(FT_M, FT_PN, 0), idesc_x = tc_idesc(FT_M, FT_XN, 0), idesc_h = tc_idesc(FT_M, 32, 0);
+            uint32_t it = 0, hq = 0;                  // hq: next pass whose heads MMA is still to be issued
+            const uint32_t hb_addr = smem_u32(sHB);
+            // heads: (pi_hat, y logits) += relu(h_t)[:, 16 units of pass q] . W_heads[16 units][32]; the A tile is read
+            // from tensor memory (written by the epilogue warps with tcgen05.st: no shared-memory staging, no proxy
+            // fence); issued three passes behind the gate MMAs, when the tile has certainly been written
+            auto issue_heads = [&](uint32_t q) {
+                const uint32_t sb = q & 1, p = q & 15, stp = q >> 4;
+                mbar_wait(&stage_full[sb], (q >> 1) & 1);
+                tc_fence_after();
+                tc_mma_ts(tmem_base + 128 + (stp & 1) * 32, tmem_base + 192 + sb * 8, tc_smem_desc_k16(hb_addr + p * 1024),
+                          idesc_h, p != 0);
+                tc_commit(&stage_empty[sb]);
+                if (p == 15) tc_commit(&heads_full[stp & 1]);
+            };
             int cur = 0;
             for (int t = L - 1, step = 0; t >= 0; --t, ++step) {
                 if (step > 0) { mbar_wait(&a_ready, (step - 1) & 1); }
@@ -176,13 +198,19 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                     }
                     tc_commit(&b_empty[s]);
                     tc_commit(&acc_full[a]);
+                    while (hq + 3 <= it) issue_heads(hq++);
                 }
+                // the step's last heads MMAs: must not wait for the next step (the epilogue warps need the tile
+                // buffers back to finish this one)
+                while (hq < it) issue_heads(hq++);
                 cur ^= 1;
             }
         }
     } else {
-        // ===================== epilogue warps 0..7 ===================================================
-        const int q = warp & 3, hf = warp >> 2;
+        // ===================== epilogue warps: set 0 (warps 0..7) takes the even passes / accumulator 0,
+        // set 1 (warps 8..15) the odd passes / accumulator 1.  A pass is one long dependent chain per warp
+        // (LDTM -> gates -> pack -> stores); two sets in flight give every scheduler four warps to interleave.
+        const int set = warp >> 3, q = warp & 3, hf = (warp >> 2) & 1;
         const int rl = q * 32 + lane;                 // row within the tile == TMEM lane
         const int row = row0 + rl;
         const bool rv = row < R;
@@ -191,11 +219,14 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
         const size_t R32 = ((size_t)R + 31) >> 5;             // 32-row blocks of the RB32 layout
         const size_t gs = (size_t)L * R32 * 32 * LPG_H;       // elements per saved factor plane
         const size_t Rp = ((size_t)R + 63) & ~(size_t)63;     // rows padded to the 64-token image blocks
-        uint32_t it = 0;
         int cur = 0;
-        for (int t = L - 1; t >= 0; --t) {
+        float b_heads[1 + LPG_Y];
+        b_heads[0] = lpg[o.b_pi];
+#pragma unroll
+        for (int c = 0; c < LPG_Y; ++c) b_heads[1 + c] = lpg[o.b_y + c];
+        for (int t = L - 1, step = 0; t >= 0; --t, ++step) {
             // x_{t-1} (the next processed step) goes into the other x tile as fp16 (one thread per row)
-            if (hf == 0 && t > 0) {
+            if (set == 0 && hf == 0 && t > 0) {
                 uint4 pk = make_uint4(0u, 0u, 0u, 0u);
                 if (rv) {
                     const float4* xp = reinterpret_cast<const float4*>(x + ((size_t)(t - 1) * R + row) * LPG_XP);
@@ -212,12 +243,10 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
             const bool zero_next = (t > 0) && done[((size_t)n_ag * L + (t - 1)) * W + w_ag];
             const unsigned char* Acur = sA + cur * FT_ABUF;
             unsigned char* Anxt = sA + (cur ^ 1) * FT_ABUF;
-            float head[1 + LPG_Y];
-#pragma unroll
-            for (int c = 0; c < 1 + LPG_Y; ++c) head[c] = 0.0f;
             const size_t tokbase = rb32_index((size_t)t, R32, rsafe, 0);
-            for (int p = 0; p < FT_NPASS; ++p, ++it) {
-                const int a = it & 1;
+            for (int p = set; p < FT_NPASS; p += 2) {
+                const uint32_t it = (uint32_t)step * FT_NPASS + p;
+                const int a = set;
                 mbar_wait(&acc_full[a], (it >> 1) & 1);
                 tc_fence_after();
                 float ar[8], az[8], an[8], ai[8];
@@ -246,13 +275,6 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                     hn[e] = an[e] + sbhn[u];
                     nn[e] = tanh_fast(ai[e] + rr[e] * hn[e]);
                     hv[e] = (1.0f - zz[e]) * nn[e] + zz[e] * hp[e];
-                    const float y = fmaxf(hv[e], 0.0f);
-                    head[0] = fmaf(y, swp[u], head[0]);
-                    {
-                        const float4 w0 = *reinterpret_cast<const float4*>(sWy + u * LPG_Y), w1 = *reinterpret_cast<const float4*>(sWy + u * LPG_Y + 4);
-                        head[1] = fmaf(y, w0.x, head[1]); head[2] = fmaf(y, w0.y, head[2]); head[3] = fmaf(y, w0.z, head[3]); head[4] = fmaf(y, w0.w, head[4]);
-                        head[5] = fmaf(y, w1.x, head[5]); head[6] = fmaf(y, w1.y, head[6]); head[7] = fmaf(y, w1.z, head[7]); head[8] = fmaf(y, w1.w, head[8]);
-                    }
                 }
                 auto pack8 = [](const float (&v)[8]) {
                     uint4 r;
@@ -271,6 +293,21 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                     return r;
                 };
                 const uint4 hpk = pack8(hv);
+                {   // relu(h_t) of this pass -> K = 16 tile (8 TMEM columns) for the heads MMA
+                    const uint32_t sb = it & 1;
+                    mbar_wait(&stage_empty[sb], ((it >> 1) & 1) ^ 1);
+                    uint4 rl4;
+                    const __half2 z2 = __float2half2_rn(0.0f);
+                    const __half2* hs = reinterpret_cast<const __half2*>(&hpk);
+                    __half2 r0 = __hmax2(hs[0], z2), r1 = __hmax2(hs[1], z2), r2 = __hmax2(hs[2], z2), r3 = __hmax2(hs[3], z2);
+                    rl4.x = *reinterpret_cast<uint32_t*>(&r0); rl4.y = *reinterpret_cast<uint32_t*>(&r1);
+                    rl4.z = *reinterpret_cast<uint32_t*>(&r2); rl4.w = *reinterpret_cast<uint32_t*>(&r3);
+                    tmem_st4(tmem_base + ((uint32_t)(q * 32) << 16) + 192 + sb * 8 + hf * 4, rl4);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&stage_full[sb]);
+                }
                 *reinterpret_cast<uint4*>(Anxt + soff) = zero_next ? make_uint4(0u, 0u, 0u, 0u) : hpk;
                 if (rv) {
                     const size_t so = tokbase + ((size_t)(u0 >> 3) << 8);          // RB32: chunk stride 256 elements
@@ -296,36 +333,40 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_ready);
-            // heads: combine the two unit-halves of each row (hf = 1 -> smem -> hf = 0)
-            if (hf == 1) {
+            // heads: the 16 heads MMAs of this step are complete -> bias, softmax, outputs (one thread per row)
+            if (set == 1 && hf == 0) {
+                mbar_wait(&heads_full[step & 1], (step >> 1) & 1);
+                tc_fence_after();
+                float v[4][8];
+                const uint32_t th = tmem_base + ((uint32_t)(q * 32) << 16) + 128 + (step & 1) * 32;
 #pragma unroll
-                for (int c = 0; c < 1 + LPG_Y; ++c) shead[rl * 9 + c] = head[c];
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");          // epilogue warps only
-            if (hf == 0 && rv) {
-                const float b_pi = lpg[o.b_pi];
-                float zl[LPG_Y], pr[LPG_Y];
+                for (int j = 0; j < 4; ++j) tmem_ld8(th + 8 * j, v[j]);
+                tmem_ld_wait();
+                tc_fence_before();
+                if (rv) {
+                    float zl[LPG_Y], pr[LPG_Y];
 #pragma unroll
-                for (int c = 0; c < LPG_Y; ++c) zl[c] = head[1 + c] + shead[rl * 9 + 1 + c] + lpg[o.b_y + c];
-                softmax_c<LPG_Y>(zl, pr);
-                const size_t tok = (size_t)t * R + row;
-                pi_hat[tok] = head[0] + shead[rl * 9] + b_pi;
-                float4* yo = reinterpret_cast<float4*>(y_hat + tok * LPG_Y);
-                yo[0] = make_float4(pr[0], pr[1], pr[2], pr[3]);
-                yo[1] = make_float4(pr[4], pr[5], pr[6], pr[7]);
+                    for (int c = 0; c < 7; ++c) zl[c] = v[0][1 + c] + v[2][1 + c] + b_heads[1 + c];
+                    zl[7] = v[1][0] + v[3][0] + b_heads[8];
+                    softmax_c<LPG_Y>(zl, pr);
+                    const size_t tok = (size_t)t * R + row;
+                    pi_hat[tok] = v[0][0] + v[2][0] + b_heads[0];
+                    float4* yo = reinterpret_cast<float4*>(y_hat + tok * LPG_Y);
+                    yo[0] = make_float4(pr[0], pr[1], pr[2], pr[3]);
+                    yo[1] = make_float4(pr[4], pr[5], pr[6], pr[7]);
+                }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
             cur ^= 1;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, 128);
+    if (warp == 17) tmem_dealloc(tmem_base, 256);
 }
 
 static size_t gru_fwd_tc_smem(int X) {
     (void)X;
-    return 2 * FT_ABUF + 2 * FT_AX + FT_NS * FT_BSTAGE + sizeof(float) * (2 * LPG_H + LPG_H * LPG_Y + FT_M * 9) + 1024;
+    return 2 * FT_ABUF + 2 * FT_AX + FT_NS * FT_BSTAGE + FT_NPASS * 1024 + sizeof(float) * LPG_H + 1024;
 }
 
 extern "C" int toued_gru_forward_tc(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,

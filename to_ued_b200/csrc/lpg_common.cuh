@@ -43,8 +43,15 @@ __device__ __forceinline__ float tanhf_(float x) {
 
 // fast variants for the tensor-core epilogues (MUFU.EX2 + MUFU.RCP, ~2 ulp): the operands there are
 // fp16/bf16-rounded anyway
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
+// straight MUFU sequences (ex2.approx / rcp.approx, ~1e-7 absolute error, no slow-path range fix-ups:
+// 2^(+big) = inf -> rcp = 0, 2^(-big) = 0 -> rcp(1) = 1, which are the correct saturated values)
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// single-MUFU versions (tanh.approx.f32, max relative error 2^-11 -- the precision of the fp16 hidden state)
+__device__ __forceinline__ float tanh_mufu(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_mufu(float x) { return fmaf(0.5f, tanh_mufu(0.5f * x), 0.5f); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.0f, rcp_approx(1.0f + ex2_approx(-2.8853900817779268f * x)), -1.0f); }
 
 // softmax over C values (true expf; float path, tolerance-checked)
 template <int C>

@@ -17,7 +17,9 @@ template <int N, int K>
 __global__ void __launch_bounds__(128, 1)
 tc_gemm_test_kernel(const float* __restrict__ A, const __half* __restrict__ Bimg, float* __restrict__ D) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // (offset arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared
+    //  address space and emits LDS / STS instead of generic LD / ST)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* sA = smem;                              // K/64 K-blocks x 128 rows x 128 B
     unsigned char* sB = smem + (K / 64) * 128 * 128;       // K/64 K-blocks x N rows x 128 B
     __shared__ __align__(8) uint64_t bar_b, bar_mma;
@@ -94,7 +96,9 @@ __global__ void __launch_bounds__(128, 1)
 tc_gemm_mn_test_kernel(const unsigned char* __restrict__ Aimg, const unsigned char* __restrict__ Bimg, float* __restrict__ D,
                        uint32_t lbo, uint32_t sbo, uint32_t kadv) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // (offset arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared
+    //  address space and emits LDS / STS instead of generic LD / ST)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* sA = smem;               // 2 token blocks x [2 col groups][8 KB]
     unsigned char* sB = smem + 32768;
     __shared__ __align__(8) uint64_t bar_ld, bar_mma;
@@ -169,7 +173,9 @@ __global__ void __launch_bounds__(128, 1)
 tc_gemm_mixed_test_kernel(const float* __restrict__ A, const __half* __restrict__ Bimg, float* __restrict__ D) {
     constexpr int N = 48, K = 272;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // (offset arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared
+    //  address space and emits LDS / STS instead of generic LD / ST)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* sA = smem;                               // 4 x 16 KB SW128 + 4 KB k16 tile
     unsigned char* sAx = sA + 4 * 128 * 128;
     unsigned char* sB = sAx + 4096;                         // 4 x 6 KB SW128 + 1.5 KB k16 tile (1024-aligned)

@@ -23,7 +23,9 @@ wgrad_wh_tc_kernel(const unsigned char* __restrict__ hpimg, const unsigned char*
                    const unsigned char* __restrict__ ximg, float* __restrict__ partial, float* __restrict__ small_partial,
                    int n_tok_blocks, int blocks_per_split, int accumulate) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // (offset arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared
+    //  address space and emits LDS / STS instead of generic LD / ST)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ __align__(8) uint64_t full[WT_NS], empty[WT_NS], done_bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(HM_THREADS, 1)
 wgrad_heads_mma_kernel(const __half* __restrict__ h16, const float* __restrict__ d_pi_hat, const float* __restrict__ dl,
                        float* __restrict__ partial, int R, int L, int blocks_per_split, int accumulate) {
     extern __shared__ __align__(1024) unsigned char hm_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(hm_raw) + 127) & ~uintptr_t(127));
+    unsigned char* smem = hm_raw + ((128u - (smem_u32(hm_raw) & 127u)) & 127u);
     __shared__ __align__(8) uint64_t full[HM_NS], ready[HM_NS], empty[HM_NS], done_bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
