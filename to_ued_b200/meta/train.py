@@ -163,9 +163,14 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     eval_done = [None] * S
     eval_stream = _side_streams(dev, S + 1)[S] if S > 1 else _eval_stream(dev)
 
-    for mb in range(num_mini_batches):
+    # The host enqueues the forward chains of a group of S mini-batches first and their reverse chains second,
+    # so every stream has work within about a millisecond of the step's start (enqueueing one mini-batch's
+    # whole chain before the next would leave the other streams idle for the first few milliseconds).
+    ctx = {}
+
+    def forward_phase(mb):
         slot = mb % S
-        ws, tape, msum = wss[slot], wss[slot].tape, msums[slot]
+        ws, tape = wss[slot], wss[slot].tape
         with torch.cuda.stream(streams[slot]):
             if S > 1 and mb < S:
                 streams[slot].wait_event(ready)
@@ -201,6 +206,14 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                 returns[sl] = eval_agent(r_evalagent[sl], rollout_manager, levels, tape.actor[K], eval_workers)
                 eval_done[slot] = torch.cuda.Event()
                 eval_done[slot].record(eval_stream)
+            ctx[mb] = (sl, sub2, state, am, levels)
+
+    def backward_phase(mb):
+        slot = mb % S
+        ws, tape, msum = wss[slot], wss[slot].tape, msums[slot]
+        sl, sub2, state, am, levels = ctx.pop(mb)
+        with torch.cuda.stream(streams[slot]):
+            s = _lib.stream_ptr()
             # ---- value "update" (Q2) + advantage + LPG loss + lam_K (meta/train.py:60-100) ----
             vparams = value_critic_states.params[sl]
             _lib.call("toued_meta_loss", p(tape.obs[K]), p(tape.action[K]), p(tape.reward[K]), p(tape.done[K]),
@@ -243,6 +256,13 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
             new_step[sl] = sub2.actor_state.step
             new_state[sl] = state
             new_obs[sl] = tape.obs[K][:, -1]
+
+    for g0 in range(0, num_mini_batches, S):
+        group = range(g0, min(num_mini_batches, g0 + S))
+        for mb in group:
+            forward_phase(mb)
+        for mb in group:
+            backward_phase(mb)
     for st in ([] if S == 1 else list(streams)) + [eval_stream]:
         ev = torch.cuda.Event()
         ev.record(st)
