@@ -17,7 +17,7 @@
 #include "../../include/toued.h"
 
 constexpr int BT_M = 128;
-constexpr int BT_THREADS = 320;
+constexpr int BT_THREADS = 352;            // 8 epilogue warps + TMA-load warp + MMA warp + TMA-store warp
 constexpr int BT_ACHUNK = BT_M * 128;            // 16 KB: [128 rows][64 bf16]
 constexpr int BT_ASTAGE = 6 * BT_ACHUNK;         // dG_r, dG_z, dG_hn, cz_hi, cz_lo, dG_an (store only)
 constexpr int BT_BCHUNK = LPG_H * 128;           // 32 KB: [256 units][64 c]
@@ -73,7 +73,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
     float* sWi = sWy + LPG_H * LPG_Y;                           // [256 units][8]: Wi rows 3, 4 x gates (r, z, n), 2 pad
     float* sdx = sWi + LPG_H * 8;                               // [128][2]
     unsigned char* ssign = reinterpret_cast<unsigned char*>(sdx + BT_M * 2);   // [16 chunks][256 threads]: relu'(h_t) bits
-    __shared__ __align__(8) uint64_t b_full[BT_NSB], b_empty[BT_NSB], a_full, a_empty, q_full;
+    __shared__ __align__(8) uint64_t b_full[BT_NSB], b_empty[BT_NSB], k_full[4], a_empty, q_full;
     __shared__ uint32_t tmem_base_s;
 
     const LpgOffsets o = lpg_offsets(X);
@@ -82,7 +82,8 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
 
     if (tid == 0) {
         for (int s = 0; s < BT_NSB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        mbar_init(&a_full, 8); mbar_init(&a_empty, 2); mbar_init(&q_full, 1);
+        for (int k = 0; k < 4; ++k) mbar_init(&k_full[k], 4);
+        mbar_init(&a_empty, 2); mbar_init(&q_full, 1);
         mbar_fence_init();
     }
     if (warp == 9) tmem_alloc(&tmem_base_s, 512);
@@ -121,38 +122,61 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
             constexpr uint32_t idesc256 = tc_idesc(BT_M, 256, 1), idesc64 = tc_idesc(BT_M, 64, 1);
             const uint32_t a_addr = smem_u32(sA), i_addr = smem_u32(sI);
             uint32_t it = 0;
-            const size_t Rp = ((size_t)R + 63) & ~(size_t)63;
-            const int nsub = ((size_t)row0 + 64 < Rp) ? 2 : 1;      // 64-token sub-tiles of this CTA inside the image
             uint32_t ait = 0;
             for (int t = 0; t < L; ++t) {
                 const uint32_t q_addr = tmem_base + (t & 1) * 256;
                 const bool mma = t + 1 < L;                          // the last step only stores its dG tiles
                 for (int ub = 0; ub < 4; ++ub, ++ait) {
-                    mbar_wait(&a_full, ait & 1);
-                    tc_fence_after();
+                    // The A stage is consumed K-step by K-step (16 units = what four epilogue warps finish every two
+                    // chunks): the MMAs of a unit block are spread over the time the epilogue warps need to produce
+                    // it, so that only the last quarter is still outstanding when they want the stage back.
+                    uint32_t sg[3];
                     if (mma) {
+#pragma unroll
                         for (int g = 0; g < 3; ++g, ++it) {
-                            const int s = it % BT_NSB;
-                            mbar_wait(&b_full[s], (it / BT_NSB) & 1);
-                            tc_fence_after();
-                            const uint64_t ad = tc_smem_desc(a_addr + g * BT_ACHUNK);
-                            const uint64_t bd = tc_smem_desc(smem_u32(sB + s * BT_BCHUNK));
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) tc_mma(q_addr, ad + 2 * ks, bd + 2 * ks, idesc256, (ub | g | ks) != 0);
-                            tc_commit(&b_empty[s]);
-                        }
-                        // z * dh_t (bf16 hi + lo) through the identity: accumulates onto columns [64 ub, 64 ub + 64)
-                        const uint64_t idd = tc_smem_desc(i_addr);
-#pragma unroll
-                        for (int c = 3; c < 5; ++c) {
-                            const uint64_t ad = tc_smem_desc(a_addr + c * BT_ACHUNK);
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) tc_mma(q_addr + ub * 64, ad + 2 * ks, idd + 2 * ks, idesc64, 1u);
+                            sg[g] = it % BT_NSB;
+                            mbar_wait(&b_full[sg[g]], (it / BT_NSB) & 1);
                         }
                     }
+                    const uint64_t idd = tc_smem_desc(i_addr);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int ks = ((kk & 1) << 1) | (kk >> 1);      // 0, 2, 1, 3: the two unit halves progress together
+                        mbar_wait(&k_full[ks], ait & 1);
+                        tc_fence_after();
+                        if (mma) {
+#pragma unroll
+                            for (int g = 0; g < 3; ++g)
+                                tc_mma(q_addr, tc_smem_desc(a_addr + g * BT_ACHUNK) + 2 * ks,
+                                       tc_smem_desc(smem_u32(sB + sg[g] * BT_BCHUNK)) + 2 * ks, idesc256, (ub | kk | g) != 0);
+                            // z * dh_t (bf16 hi + lo) through the identity: accumulates onto columns [64 ub, 64 ub + 64)
+                            tc_mma(q_addr + ub * 64, tc_smem_desc(a_addr + 3 * BT_ACHUNK) + 2 * ks, idd + 2 * ks, idesc64, 1u);
+                            tc_mma(q_addr + ub * 64, tc_smem_desc(a_addr + 4 * BT_ACHUNK) + 2 * ks, idd + 2 * ks, idesc64, 1u);
+                        }
+                    }
+                    if (mma) {
+#pragma unroll
+                        for (int g = 0; g < 3; ++g) tc_commit(&b_empty[sg[g]]);
+                    }
                     tc_commit(&a_empty);                             // arrival 1 of 2: the MMAs have read the stage
-                    // dG tiles of this unit block -> token-tile image for the weight-gradient GEMM: the SW128
-                    // chunks in smem ARE the image's 8 KB sub-tiles, so they leave as full-line TMA bulk stores
+                }
+                if (mma) tc_commit(&q_full);
+            }
+        }
+    } else if (warp == 10) {
+        // ===================== TMA store warp: dG tiles of every unit block -> token-tile image ==========
+        // The SW128 chunks in smem ARE the image's 8 KB sub-tiles of the weight-gradient GEMM, so they leave as
+        // full-line bulk stores.  A warp of its own: waiting for the stores to finish reading the stage must not
+        // hold up the MMA issue of the next unit block.
+        if (lane == 0) {
+            const uint32_t a_addr = smem_u32(sA);
+            const size_t Rp = ((size_t)R + 63) & ~(size_t)63;
+            const int nsub = ((size_t)row0 + 64 < Rp) ? 2 : 1;      // 64-token sub-tiles of this CTA inside the image
+            uint32_t ait = 0;
+            for (int t = 0; t < L; ++t) {
+                for (int ub = 0; ub < 4; ++ub, ++ait) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) mbar_wait(&k_full[ks], ait & 1);
                     const size_t itok0 = (size_t)t * Rp + row0;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -164,7 +188,6 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                     bulk_wait_read();
                     mbar_arrive(&a_empty);                           // arrival 2 of 2: the stores have read the stage
                 }
-                if (mma) tc_commit(&q_full);
             }
             bulk_wait_all();
         }
@@ -316,11 +339,13 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                     st_shared_v4(so + 3 * BT_ACHUNK, pack8bf(czh));
                     st_shared_v4(so + 4 * BT_ACHUNK, pack8bf(czl));
                     st_shared_v4(so + 5 * BT_ACHUNK, pack8bf(gan));
+                    if (c8 & 1) {                                  // K-step 2 hf + (c8 >> 1) of this unit block is complete
+                        fence_proxy_async_smem();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&k_full[2 * hf + (c8 >> 1)]);
+                    }
                 }
-                fence_proxy_async_smem();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&a_full);
                 ++ait;
             }
             // d pyt / d pyt1: combine the two unit halves of the row
