@@ -259,26 +259,44 @@ def run_ours(a):
         pass
     per_launch_agents = AGENTS_PER_GPU // mini_batches
     tokens = per_launch_agents * W * L
-    flops = {   # algorithmic FLOPs per launch
+    flops = {   # algorithmic FLOPs per launch (2*256*768 per token for each GRU contraction + heads)
         "toued_gru_forward": tokens * 400896.0,
         "toued_gru_backward": per_launch_agents * W * (L - 1) * 2.0 * 768 * 256 + tokens * 2.0 * 256 * 9,
         "toued_lpg_wgrad": tokens * (2.0 * 256 * 768 + 2.0 * 8 * 768 + 2.0 * 256 * 9),
         "toued_gru_forward_tc": tokens * 400896.0,
-        "toued_gru_backward_tc": per_launch_agents * W * (L - 1) * 2.0 * (768 + 2 * 64) * 256 + tokens * 2.0 * 256 * 9,
+        "toued_gru_backward_tc": per_launch_agents * W * (L - 1) * 2.0 * 768 * 256 + tokens * 2.0 * 256 * 9,
         "toued_lpg_wgrad_tc": tokens * (2.0 * 256 * 768 + 2.0 * 8 * 768 + 2.0 * 256 * 9),
     }
+    # algorithmic HBM bytes per token the tensor-core kernels must move (fp16 gate planes + h,
+    # bf16 dG / h' images) -- reported next to the tensor roofline because the activations do not fit on chip
+    hbm_bytes = {"toued_gru_forward_tc": tokens * (32.0 + 4 * 512 + 512 + 512 + 36),
+                 "toued_gru_backward_tc": tokens * (4 * 512 + 512 + 72 + 2048 + 40.0),
+                 "toued_lpg_wgrad_tc": tokens * (2048 + 512 + 512 + 128 + 36.0)}
     total_prof = sum(ms for _, ms in prof.values()) or 1.0
     shares = {k: {"calls": c, "ms_per_step": ms / PROF_STEPS, "share": ms / total_prof} for k, (c, ms) in prof.items()}
     dom = max((k for k in prof if k in flops), key=lambda k: prof[k][1])
     calls, ms = prof[dom]
     achieved = flops[dom] / (ms / calls * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/), scaled to this
+    # launch size (the capture records bytes per token)
+    traffic = None
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
+        traffic = ncu["kernels"][dom]["dram_bytes_per_token"] * tokens
+    except Exception:
+        pass
     roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "agents_per_launch": per_launch_agents,
+                "frac": achieved / peak, "traffic": traffic, "agents_per_launch": per_launch_agents,
                 "ms_per_launch": ms / calls,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback",
                 "note": ("tcgen05 path (fp16/bf16 operands, fp32 accumulate in TMEM)" if precision == "tc" else
                          "exact-fp32 SIMT GRU path") + "; FLOPs = algorithmic GRU/head/weight-gradient FLOPs per launch"}
+    if dom in hbm_bytes:
+        gbs = hbm_bytes[dom] / (ms / calls * 1e-3) / 1e9
+        roofline["hbm"] = {"achieved": gbs, "peak": peaks.get("hbm_gbs", 6556.8), "unit": "GB/s",
+                           "frac": gbs / peaks.get("hbm_gbs", 6556.8),
+                           "note": "algorithmic activation bytes of the same kernel (saved gates / dG image round trips)"}
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
     cpu = None
