@@ -129,11 +129,11 @@ def lpg_agent_train_step(k, tape: Tape, levels, step, lpg_params, lifetime_condi
     tape.scal_sum += tape.scalars[a]
 
 
-def train_lpg_agent(rng, lpg_train_state, agent_state: AgentState, rollout_manager, num_train_steps: int,
-                    agent_target_coeff: float, tape: Optional[Tape] = None, lpg_stride: int = 0):
-    """agents/lpg_agent.py:88-140, batched: rng uint32[N, 2].
-    Returns (agent_state, rollouts (list of Transition; all K only when the tape records), LPGAgentMetrics
-    of f32[N]).  ``lpg_stride`` != 0: ``lpg_train_state`` holds one parameter vector per agent."""
+def train_lpg_agent_steps(rng, lpg_train_state, agent_state: AgentState, rollout_manager, num_train_steps: int,
+                          agent_target_coeff: float, tape: Optional[Tape] = None, lpg_stride: int = 0):
+    """``train_lpg_agent`` as a generator: yields after the set-up and after every update (nothing is yielded but
+    control), returns the result tuple.  Lets a caller that drives several agent chunks on different CUDA streams
+    enqueue their updates round-robin; every resumption must happen under the chunk's own stream context."""
     env = rollout_manager.env
     actor, critic = agent_state.actor_state, agent_state.critic_state
     N, W = agent_state.env_state.packed.shape
@@ -148,19 +148,20 @@ def train_lpg_agent(rng, lpg_train_state, agent_state: AgentState, rollout_manag
     tape.critic[0].copy_(critic.params)
     tape.scal_sum.zero_()
     keys_d = prng.chain_device(prng.to_device(rng, dev), K)   # lpg_agent.py:104-105, derived on the device
-    s = _lib.stream_ptr()
     p = _lib.ptr
     lpg = lpg_train_state.params if hasattr(lpg_train_state, "params") else lpg_train_state
     cond = lpg_train_state.model.lifetime_conditioning if hasattr(lpg_train_state, "model") else False
     if tape.precision == "tc" and not lpg_stride:             # recurrent matrix -> fp16 SW128 pass images
-        _lib.call("toued_pack_wh_forward", p(lpg), p(tape.wh_img), int(cond), s)
+        _lib.call("toued_pack_wh_forward", p(lpg), p(tape.wh_img), int(cond), _lib.stream_ptr())
+    yield
     for k in range(K):
         r = tape.ri(k)
         _lib.call("toued_rollout", p(levels), p(keys_d[k]), p(tape.actor[tape.ti(k)]), None, p(state), p(tape.obs[r]),
                   p(tape.action[r]), p(tape.reward[r]), p(tape.done[r]), None, N, W, L, env.obs_dim,
-                  env.max_grid_size, env.max_n_objs, 0, s)
+                  env.max_grid_size, env.max_n_objs, 0, _lib.stream_ptr())
         lpg_agent_train_step(k, tape, levels, step, lpg, cond, agent_target_coeff, actor.learning_rate,
                              critic.learning_rate, actor.max_grad_norm, lpg_stride=lpg_stride)
+        yield
     sc = tape.scal_sum / K                                    # lpg_agent.py:140 mean over updates
     metrics = LPGAgentMetrics(policy_l2=sc[:, 4], policy_entropy=sc[:, 6], critic_loss=sc[:, 3],
                               critic_l2=sc[:, 5], critic_entropy=sc[:, 7])
@@ -171,3 +172,17 @@ def train_lpg_agent(rng, lpg_train_state, agent_state: AgentState, rollout_manag
         env_obs=tape.obs[tape.ri(K - 1)][:, -1].clone(), env_state=EnvState(state, env.max_n_objs))
     rollouts = [tape.transition(k) for k in range(K)] if tape.record else [tape.transition(K - 1)]
     return new_agent, rollouts, metrics
+
+
+def train_lpg_agent(rng, lpg_train_state, agent_state: AgentState, rollout_manager, num_train_steps: int,
+                    agent_target_coeff: float, tape: Optional[Tape] = None, lpg_stride: int = 0):
+    """agents/lpg_agent.py:88-140, batched: rng uint32[N, 2].
+    Returns (agent_state, rollouts (list of Transition; all K only when the tape records), LPGAgentMetrics
+    of f32[N]).  ``lpg_stride`` != 0: ``lpg_train_state`` holds one parameter vector per agent."""
+    gen = train_lpg_agent_steps(rng, lpg_train_state, agent_state, rollout_manager, num_train_steps,
+                                agent_target_coeff, tape=tape, lpg_stride=lpg_stride)
+    while True:
+        try:
+            next(gen)
+        except StopIteration as done:
+            return done.value

@@ -24,7 +24,7 @@ import torch
 from .. import _lib
 from ..util import prng
 from ..util.data import AgentState, LpgHyperparams
-from ..agents.lpg_agent import Tape, train_lpg_agent
+from ..agents.lpg_agent import Tape, train_lpg_agent, train_lpg_agent_steps
 from ..agents.agents import eval_agent
 from ..environments.gridworld.gridworld import EnvState
 
@@ -163,12 +163,13 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     eval_done = [None] * S
     eval_stream = _side_streams(dev, S + 1)[S] if S > 1 else _eval_stream(dev)
 
-    # The host enqueues the forward chains of a group of S mini-batches first and their reverse chains second,
-    # so every stream has work within about a millisecond of the step's start (enqueueing one mini-batch's
-    # whole chain before the next would leave the other streams idle for the first few milliseconds).
-    ctx = {}
+    # The host enqueues the chains of a group of S mini-batches round-robin, one agent update at a time (forward:
+    # k = 0..K-1, reverse: k = K-1..0), so every stream has work from the start of the step and the chains finish
+    # together (enqueueing one mini-batch's whole chain before the next would leave the other streams idle for
+    # the first milliseconds and alone for the last).
+    ctx, gens = {}, {}
 
-    def forward_phase(mb):
+    def forward_begin(mb):
         slot = mb % S
         ws, tape = wss[slot], wss[slot].tape
         with torch.cuda.stream(streams[slot]):
@@ -188,9 +189,31 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                              _sub_level(agent_states.level, sl), agent_states.env_obs[sl],
                              EnvState(agent_states.env_state.packed[sl], env.max_n_objs))
             levels = sub.level.packed
-            # ---- K agent updates (forward, taped) ----
-            sub2, _, am = train_lpg_agent(r_train[sl], lpg_train_state, sub, rollout_manager, K,
-                                          lpg_hypers.agent_target_coeff, tape=tape)
+            # ---- K agent updates (forward, taped): set-up now, the updates are driven by forward_step ----
+            gens[mb] = (train_lpg_agent_steps(r_train[sl], lpg_train_state, sub, rollout_manager, K,
+                                              lpg_hypers.agent_target_coeff, tape=tape), sl, levels)
+            next(gens[mb][0])
+
+    def forward_step(mb):
+        with torch.cuda.stream(streams[mb % S]):
+            try:
+                next(gens[mb][0])
+            except StopIteration as fin:
+                gens[mb] = (fin.value,) + gens[mb][1:]
+
+    def forward_end(mb):
+        slot = mb % S
+        ws, tape = wss[slot], wss[slot].tape
+        res, sl, levels = gens.pop(mb)
+        with torch.cuda.stream(streams[slot]):
+            s = _lib.stream_ptr()
+            if not isinstance(res, tuple):                   # run the generator to its return value
+                try:
+                    while True:
+                        next(res)
+                except StopIteration as fin:
+                    res = fin.value
+            sub2, _, am = res
             # ---- rollout the updated agent (meta/train.py:46-58) ----
             state = sub2.env_state.packed
             _lib.call("toued_rollout", p(levels), p(r_eval[sl]), p(tape.actor[K]), None, p(state), p(tape.obs[K]),
@@ -208,10 +231,10 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                 eval_done[slot].record(eval_stream)
             ctx[mb] = (sl, sub2, state, am, levels)
 
-    def backward_phase(mb):
+    def backward_begin(mb):
         slot = mb % S
-        ws, tape, msum = wss[slot], wss[slot].tape, msums[slot]
-        sl, sub2, state, am, levels = ctx.pop(mb)
+        ws, tape = wss[slot], wss[slot].tape
+        sl = ctx[mb][0]
         with torch.cuda.stream(streams[slot]):
             s = _lib.stream_ptr()
             # ---- value "update" (Q2) + advantage + LPG loss + lam_K (meta/train.py:60-100) ----
@@ -220,8 +243,14 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                       p(tape.sorted_tok[K]), p(vparams), p(tape.actor[K]), p(ws.lam), p(ws.mu), p(ws.loss_scal),
                       nb, W, L, D, vparams.shape[-1], float(gamma), float(gae_lambda), float(gscale),
                       int(outer_product_quirk), s)
-            # ---- reverse pass ----
-            for k in reversed(range(K)):
+
+    def backward_step(mb, k):
+        slot = mb % S
+        ws, tape = wss[slot], wss[slot].tape
+        with torch.cuda.stream(streams[slot]):
+            s = _lib.stream_ptr()
+            # ---- reverse pass, update k ----
+            if True:
                 _lib.call("toued_agent_backward", p(tape.obs[k]), p(tape.action[k]), p(tape.sorted_tok[k]),
                           p(tape.pi_hat[k]), p(tape.y_hat[k]), p(tape.actor[k]), p(tape.critic[k]),
                           p(tape.actor[k + 1]), p(tape.critic[k + 1]), p(tape.scalars[k]), p(ws.lam), p(ws.mu),
@@ -244,6 +273,12 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                     _lib.call("toued_lpg_wgrad", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg), p(tape.x[k]),
                               p(tape.h[k]), p(tape.gates[k]), p(ws.d_pi_hat), p(ws.dl), p(ws.dx), p(ws.partials),
                               nb, W, L, D, cond, 0 if first else 1, s)
+
+    def backward_end(mb):
+        slot = mb % S
+        ws, tape, msum = wss[slot], wss[slot].tape, msums[slot]
+        sl, sub2, state, am, levels = ctx.pop(mb)
+        with torch.cuda.stream(streams[slot]):
             # ---- metrics (sums over agents; divided by n_global after the all-reduce) ----
             lpg_loss, value_loss = ws.loss_scal[:, 0], ws.loss_scal[:, 1]
             reg = (lpg_loss - lpg_hypers.policy_entropy_coeff * am.policy_entropy + lpg_hypers.policy_l2_coeff * am.policy_l2
@@ -260,9 +295,19 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     for g0 in range(0, num_mini_batches, S):
         group = range(g0, min(num_mini_batches, g0 + S))
         for mb in group:
-            forward_phase(mb)
+            forward_begin(mb)
+        for k in range(K):
+            for mb in group:
+                forward_step(mb)
         for mb in group:
-            backward_phase(mb)
+            forward_end(mb)
+        for mb in group:
+            backward_begin(mb)
+        for k in reversed(range(K)):
+            for mb in group:
+                backward_step(mb, k)
+        for mb in group:
+            backward_end(mb)
     for st in ([] if S == 1 else list(streams)) + [eval_stream]:
         ev = torch.cuda.Event()
         ev.record(st)
