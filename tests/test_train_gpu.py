@@ -62,3 +62,34 @@ def test_lpg_init_shapes_and_orthogonality(built_lib):
     np.testing.assert_allclose((hr.T @ hr).numpy(), np.eye(256), atol=1e-4)   # orthogonal recurrent init
     assert named["LPGGRU_0"]["GRUCell_0"]["ir"]["kernel"].shape == (7, 256)
     assert float(named["MLP_0"]["Dense_0"]["bias"].abs().sum()) == 0.0
+
+
+def test_log_writes_checkpoints_and_restore_resumes_bitwise(built_lib, tmp_path, monkeypatch):
+    """--log (reference train.py:63-69 + logging.py) and the restore the reference lacks: a restored LPG state
+    continues exactly like the original (same Adam moments and step count)."""
+    import os
+    import train
+    from to_ued_b200.experiments import logging as tlog
+    from to_ued_b200.experiments.parse_args import parse_args
+    from to_ued_b200.meta.meta import create_lpg_train_state
+    monkeypatch.setenv("TOUED_LOG_DIR", str(tmp_path))
+    argv = ["--env_mode", "debug", "--num_agents", "4", "--num_mini_batches", "2", "--train_steps", "3",
+            "--num_agent_updates", "3", "--score_function", "frozen", "--buffer_size", "8", "--log", "--wandb_group", "t"]
+    hist, ts, buf = train.main(argv)
+    run = [d for d in os.listdir(tmp_path) if d.startswith("t-")][0]
+    ck = os.path.join(tmp_path, run, "checkpoints")
+    assert sorted(os.listdir(ck)) == ["buffer_3.npz", "checkpoint_3.npz"]
+    args = parse_args(argv)
+    fresh = create_lpg_train_state(prng.split(prng.PRNGKey(123), 3)[1], args)
+    back = tlog.restore_checkpoint(os.path.join(ck, "checkpoint_3.npz"), fresh)
+    assert torch.equal(back.params, ts.params) and back.opt_state["count"] == 3 and back.step == ts.step
+    assert torch.equal(back.opt_state["mu"], ts.opt_state["mu"])
+    b2 = tlog.restore_buffer(os.path.join(ck, "buffer_3.npz"))
+    assert np.array_equal(b2.score, buf.score) and np.array_equal(b2.level.env_params.walls, buf.level.env_params.walls)
+    # one more Adam step from the restored and from the original state gives identical parameters
+    g = torch.randn_like(ts.params)
+    p1, p2 = ts.params.clone(), back.params.clone()
+    s1 = ts.tx.update_(p1, g, {**ts.opt_state, "mu": ts.opt_state["mu"].clone(), "nu": ts.opt_state["nu"].clone()})
+    s2 = back.tx.update_(p2, g, {**back.opt_state, "mu": back.opt_state["mu"].clone(), "nu": back.opt_state["nu"].clone()})
+    torch.cuda.synchronize()
+    assert torch.equal(p1, p2) and s1["count"] == s2["count"] == 4

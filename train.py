@@ -81,13 +81,17 @@ def _to_float(m):
 
 def run_training_experiment(args):
     rank, world = _init_distributed()
-    if args.log and rank == 0:
-        print("[to_ued_b200] --log: WandB logging is out of scope on this build; metrics are printed instead")
+    if args.log and rank == 0:                       # train.py:63-64 (local run directory instead of WandB)
+        from to_ued_b200.experiments.logging import init_logger
+        print(f"[to_ued_b200] --log: run directory {init_logger(args)}")
     train_fn = make_train(args, rank, world)
     metrics, train_state, level_buffer = train_fn(prng.PRNGKey(args.seed))
     torch.cuda.synchronize()
     if rank == 0:
         print([_to_float(m) for m in metrics])
+        if args.log:                                 # train.py:68-69
+            from to_ued_b200.experiments.logging import log_results
+            print("[to_ued_b200] checkpoints:", log_results(args, metrics, train_state, level_buffer))
     return metrics, train_state, level_buffer
 
 
