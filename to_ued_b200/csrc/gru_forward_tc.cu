@@ -93,7 +93,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
     unsigned char* sHB = sB + FT_NS * FT_BSTAGE;                // 16 x 1 KB   head weights [w_pi | W_y] as fp16 hi / lo, per pass
     float* sbhn = reinterpret_cast<float*>(sHB + FT_NPASS * 1024);    // [256]
     __shared__ __align__(8) uint64_t b_full[FT_NS], b_empty[FT_NS], acc_full[2], acc_empty[2], a_ready;
-    __shared__ __align__(8) uint64_t stage_full[2], stage_empty[2], heads_full[2];
+    __shared__ __align__(8) uint64_t stage_full[4], stage_empty[4], heads_full[2];
     __shared__ uint32_t tmem_base_s;
 
     const LpgOffsets o = lpg_offsets(X);
@@ -104,10 +104,11 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
         for (int s = 0; s < FT_NS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
         mbar_init(&a_ready, 16);
-        for (int a = 0; a < 2; ++a) { mbar_init(&stage_full[a], 8); mbar_init(&stage_empty[a], 1); mbar_init(&heads_full[a], 1); }
+        for (int a = 0; a < 4; ++a) { mbar_init(&stage_full[a], 8); mbar_init(&stage_empty[a], 1); }
+        for (int a = 0; a < 2; ++a) mbar_init(&heads_full[a], 1);
         mbar_fence_init();
     }
-    if (warp == 17) tmem_alloc(&tmem_base_s, 256);     // 2 x 64 gate accumulators + 2 x 32 head accumulators + 2 x 8 relu(h) tiles
+    if (warp == 17) tmem_alloc(&tmem_base_s, 256);     // 2 x 64 gate accumulators + 2 x 32 head accumulators + 4 x 8 relu(h) tiles
 
     for (int i = tid; i < LPG_H; i += FT_THREADS) sbhn[i] = lpg[o.bhn + i];
     // head weights as the B operand of the heads MMA: per pass a [32 n][16 k] no-swizzle block; n < 16: fp16 of
@@ -165,8 +166,8 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
             // from tensor memory (written by the epilogue warps with tcgen05.st: no shared-memory staging, no proxy
             // fence); issued three passes behind the gate MMAs, when the tile has certainly been written
             auto issue_heads = [&](uint32_t q) {
-                const uint32_t sb = q & 1, p = q & 15, stp = q >> 4;
-                mbar_wait(&stage_full[sb], (q >> 1) & 1);
+                const uint32_t sb = q & 3, p = q & 15, stp = q >> 4;      // four relu(h) tiles in flight
+                mbar_wait(&stage_full[sb], (q >> 2) & 1);
                 tc_fence_after();
                 tc_mma_ts(tmem_base + 128 + (stp & 1) * 32, tmem_base + 192 + sb * 8, tc_smem_desc_k16(hb_addr + p * 1024),
                           idesc_h, p != 0);
@@ -294,8 +295,8 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                 };
                 const uint4 hpk = pack8(hv);
                 {   // relu(h_t) of this pass -> K = 16 tile (8 TMEM columns) for the heads MMA
-                    const uint32_t sb = it & 1;
-                    mbar_wait(&stage_empty[sb], ((it >> 1) & 1) ^ 1);
+                    const uint32_t sb = it & 3;
+                    mbar_wait(&stage_empty[sb], ((it >> 2) & 1) ^ 1);
                     uint4 rl4;
                     const __half2 z2 = __float2half2_rn(0.0f);
                     const __half2* hs = reinterpret_cast<const __half2*>(&hpk);
