@@ -2,7 +2,8 @@
 //
 // A CTA owns 128 sequences (UMMA_M = 128, cta_group::1) for all L reverse-scan steps.
 //   * hidden state h' lives in shared memory as the fp16 K-major SW128 A operand (4 K-blocks x 16 KB),
-//     double-buffered: MMAs of step t read A[cur] while the epilogue writes h_t into A[nxt];
+//     single-buffered: the epilogue parks h_t in spare tensor-memory columns during the step and copies it
+//     into the A operand once the step's last MMA has read it (this frees 64 KB for two more B stages);
 //   * the recurrent matrix is pre-packed once per meta-step into fp16 SW128 "pass" images
 //     (16 passes x [3 gates x 16 units = 48 rows][256 k] = 24 KB each) and streamed from L2 by a
 //     TMA-producer warp (cp.async.bulk + mbarrier, 2 stages);
@@ -33,7 +34,8 @@ constexpr int FT_BX = (FT_XN / 8) * 256;           // 2048 B: input part (no-swi
 constexpr int FT_BSTAGE = FT_BH + FT_BX;           // 26624 B per pass image (multiple of 1024)
 constexpr int FT_AX = (FT_M / 8) * 256;            // 4096 B: x tile of the A operand
 constexpr int FT_ABUF = FT_KB * FT_M * 128;        // 65536 B
-constexpr int FT_NS = 2;                  // B stages
+constexpr int FT_NS = 4;                  // B stages
+constexpr int FT_THEADS = 256, FT_TTILE = 320, FT_THOLD = 352;   // tensor-memory columns: 4 x 64 gate accumulators at 0, then these
 constexpr int FT_THREADS = 576;           // 2 sets of 8 epilogue warps (even / odd passes) + producer warp + MMA warp
 
 // Wh[k][c] (fp32, c = g*256 + unit) -> fp16 pass images: image[p][kb][row = g*16 + u][128 B swizzled]
@@ -88,11 +90,11 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
     //  address space and emits LDS / STS instead of generic LD / ST)
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* sA = smem;                                   // 2 x 64 KB   h' (SW128 K-blocks)
-    unsigned char* sAx = sA + 2 * FT_ABUF;                      // 2 x 4 KB    x tile (no-swizzle K = 16 block)
+    unsigned char* sAx = sA + FT_ABUF;                      // 2 x 4 KB    x tile (no-swizzle K = 16 block)
     unsigned char* sB = sAx + 2 * FT_AX;                        // FT_NS x 26 KB
     unsigned char* sHB = sB + FT_NS * FT_BSTAGE;                // 16 x 1 KB   head weights [w_pi | W_y] as fp16 hi / lo, per pass
     float* sbhn = reinterpret_cast<float*>(sHB + FT_NPASS * 1024);    // [256]
-    __shared__ __align__(8) uint64_t b_full[FT_NS], b_empty[FT_NS], acc_full[2], acc_empty[2], a_ready;
+    __shared__ __align__(8) uint64_t b_full[FT_NS], b_empty[FT_NS], acc_full[4], acc_empty[4], a_ready;
     __shared__ __align__(8) uint64_t stage_full[4], stage_empty[4], heads_full[2];
     __shared__ uint32_t tmem_base_s;
 
@@ -102,13 +104,13 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
 
     if (tid == 0) {
         for (int s = 0; s < FT_NS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
+        for (int a = 0; a < 4; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
         mbar_init(&a_ready, 16);
         for (int a = 0; a < 4; ++a) { mbar_init(&stage_full[a], 8); mbar_init(&stage_empty[a], 1); }
         for (int a = 0; a < 2; ++a) mbar_init(&heads_full[a], 1);
         mbar_fence_init();
     }
-    if (warp == 17) tmem_alloc(&tmem_base_s, 256);     // 2 x 64 gate accumulators + 2 x 32 head accumulators + 4 x 8 relu(h) tiles
+    if (warp == 17) tmem_alloc(&tmem_base_s, 512);     // 2 x 64 gate accumulators + 2 x 32 head accumulators + 4 x 8 relu(h) tiles + 128 columns of parked h_t  (FT_T* below)
 
     for (int i = tid; i < LPG_H; i += FT_THREADS) sbhn[i] = lpg[o.bhn + i];
     // head weights as the B operand of the heads MMA: per pass a [32 n][16 k] no-swizzle block; n < 16: fp16 of
@@ -120,7 +122,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
         *reinterpret_cast<__half*>(sHB + p * 1024 + k16_offset(n, k)) = __float2half_rn(n < 16 ? hi : w - hi);
     }
     // initial carry = 0 (both A buffers); x tiles zero, then x_{L-1} into tile 0 (twice: W_i hi / lo parts)
-    for (int i = tid; i < (2 * FT_ABUF + 2 * FT_AX) / 16; i += FT_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < (FT_ABUF + 2 * FT_AX) / 16; i += FT_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     if (tid < FT_M) {
         const int r_ = row0 + tid;
@@ -158,48 +160,56 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
         }
     } else if (warp == 17) {
         // ===================== MMA issuer ==========================================================
-        if (lane == 0) {
+        // The whole warp walks the loop (all lanes wait on the barriers); one elected lane issues.
+        {
             constexpr uint32_t idesc = tc_idesc(FT_M, FT_PN, 0), idesc_x = tc_idesc(FT_M, FT_XN, 0), idesc_h = tc_idesc(FT_M, 32, 0);
             uint32_t it = 0, hq = 0;                  // hq: next pass whose heads MMA is still to be issued
             const uint32_t hb_addr = smem_u32(sHB);
             // heads: (pi_hat, y logits) += relu(h_t)[:, 16 units of pass q] . W_heads[16 units][32]; the A tile is read
             // from tensor memory (written by the epilogue warps with tcgen05.st: no shared-memory staging, no proxy
-            // fence); issued three passes behind the gate MMAs, when the tile has certainly been written
+            // fence); issued a few passes behind the gate MMAs, when the tile has certainly been written
             auto issue_heads = [&](uint32_t q) {
                 const uint32_t sb = q & 3, p = q & 15, stp = q >> 4;      // four relu(h) tiles in flight
                 mbar_wait(&stage_full[sb], (q >> 2) & 1);
                 tc_fence_after();
-                tc_mma_ts(tmem_base + 128 + (stp & 1) * 32, tmem_base + 192 + sb * 8, tc_smem_desc_k16(hb_addr + p * 1024),
-                          idesc_h, p != 0);
-                tc_commit(&stage_empty[sb]);
-                if (p == 15) tc_commit(&heads_full[stp & 1]);
+                if (elect_one()) {
+                    tc_mma_ts(tmem_base + FT_THEADS + (stp & 1) * 32, tmem_base + FT_TTILE + sb * 8, tc_smem_desc_k16(hb_addr + p * 1024),
+                              idesc_h, p != 0);
+                    tc_commit(&stage_empty[sb]);
+                    if (p == 15) tc_commit(&heads_full[stp & 1]);
+                }
+                __syncwarp();
             };
             int cur = 0;
+            const uint32_t a_addr = smem_u32(sA);
             for (int t = L - 1, step = 0; t >= 0; --t, ++step) {
                 if (step > 0) { mbar_wait(&a_ready, (step - 1) & 1); }
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA + cur * FT_ABUF);
                 const uint64_t axd = tc_smem_desc_k16(smem_u32(sAx + cur * FT_AX));
                 for (int p = 0; p < FT_NPASS; ++p, ++it) {
-                    const int s = it % FT_NS, a = it & 1;
-                    mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+                    const int s = it % FT_NS, a = it & 3;
+                    mbar_wait(&acc_empty[a], ((it >> 2) & 1) ^ 1);
                     mbar_wait(&b_full[s], (it / FT_NS) & 1);
                     tc_fence_after();
-                    const uint32_t b_addr = smem_u32(sB + s * FT_BSTAGE);
-                    const uint32_t d_addr = tmem_base + a * 64;
-                    // input projection + bias first: initialises all 64 accumulator columns
-                    // (r | z | 0 | i_n); the recurrent part then accumulates onto columns 0..47 (r | z | h_n)
-                    tc_mma(d_addr, axd, tc_smem_desc_k16(b_addr + FT_BH), idesc_x, 0u);
+                    if (elect_one()) {
+                        const uint32_t b_addr = smem_u32(sB + s * FT_BSTAGE);
+                        const uint32_t d_addr = tmem_base + a * 64;
+                        // input projection + bias first: initialises all 64 accumulator columns
+                        // (r | z | 0 | i_n); the recurrent part then accumulates onto columns 0..47 (r | z | h_n)
+                        tc_mma(d_addr, axd, tc_smem_desc_k16(b_addr + FT_BH), idesc_x, 0u);
+                        const uint64_t ad0 = tc_smem_desc(a_addr), bd0 = tc_smem_desc(b_addr);
 #pragma unroll
-                    for (int kb = 0; kb < FT_KB; ++kb) {
-                        const uint64_t ad = tc_smem_desc(a_addr + kb * FT_M * 128);
-                        const uint64_t bd = tc_smem_desc(b_addr + kb * FT_PN * 128);
+                        for (int kb = 0; kb < FT_KB; ++kb) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) tc_mma(d_addr, ad + 2 * ks, bd + 2 * ks, idesc, 1u);
+                            for (int ks = 0; ks < 4; ++ks)      // descriptor address field is in 16-byte units
+                                tc_mma(d_addr, ad0 + (uint64_t)((kb * FT_M * 128 + ks * 32) >> 4),
+                                       bd0 + (uint64_t)((kb * FT_PN * 128 + ks * 32) >> 4), idesc, 1u);
+                        }
+                        tc_commit(&b_empty[s]);
+                        tc_commit(&acc_full[a]);
                     }
-                    tc_commit(&b_empty[s]);
-                    tc_commit(&acc_full[a]);
-                    while (hq + 3 <= it) issue_heads(hq++);
+                    __syncwarp();
+                    while (hq + 4 <= it) issue_heads(hq++);
                 }
                 // the step's last heads MMAs: must not wait for the next step (the epilogue warps need the tile
                 // buffers back to finish this one)
@@ -242,13 +252,12 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
             }
             // mask for the NEXT processed step (t-1): its carry is zero where done[t-1]
             const bool zero_next = (t > 0) && done[((size_t)n_ag * L + (t - 1)) * W + w_ag];
-            const unsigned char* Acur = sA + cur * FT_ABUF;
-            unsigned char* Anxt = sA + (cur ^ 1) * FT_ABUF;
+            const unsigned char* Acur = sA;
             const size_t tokbase = rb32_index((size_t)t, R32, rsafe, 0);
             for (int p = set; p < FT_NPASS; p += 2) {
                 const uint32_t it = (uint32_t)step * FT_NPASS + p;
-                const int a = set;
-                mbar_wait(&acc_full[a], (it >> 1) & 1);
+                const int a = it & 3;                              // accumulators {set, set + 2}: the MMAs run two passes ahead of this set
+                mbar_wait(&acc_full[a], (it >> 2) & 1);
                 tc_fence_after();
                 float ar[8], az[8], an[8], ai[8];
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a * 64 + hf * 8;
@@ -297,19 +306,20 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                 {   // relu(h_t) of this pass -> K = 16 tile (8 TMEM columns) for the heads MMA
                     const uint32_t sb = it & 3;
                     mbar_wait(&stage_empty[sb], ((it >> 2) & 1) ^ 1);
+                    // park the (masked) next carry in tensor memory until the A operand may be overwritten
+                    tmem_st4(tmem_base + ((uint32_t)(q * 32) << 16) + FT_THOLD + p * 8 + hf * 4, zero_next ? make_uint4(0u, 0u, 0u, 0u) : hpk);
                     uint4 rl4;
                     const __half2 z2 = __float2half2_rn(0.0f);
                     const __half2* hs = reinterpret_cast<const __half2*>(&hpk);
                     __half2 r0 = __hmax2(hs[0], z2), r1 = __hmax2(hs[1], z2), r2 = __hmax2(hs[2], z2), r3 = __hmax2(hs[3], z2);
                     rl4.x = *reinterpret_cast<uint32_t*>(&r0); rl4.y = *reinterpret_cast<uint32_t*>(&r1);
                     rl4.z = *reinterpret_cast<uint32_t*>(&r2); rl4.w = *reinterpret_cast<uint32_t*>(&r3);
-                    tmem_st4(tmem_base + ((uint32_t)(q * 32) << 16) + 192 + sb * 8 + hf * 4, rl4);
+                    tmem_st4(tmem_base + ((uint32_t)(q * 32) << 16) + FT_TTILE + sb * 8 + hf * 4, rl4);
                     tmem_st_wait();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&stage_full[sb]);
                 }
-                *reinterpret_cast<uint4*>(Anxt + soff) = zero_next ? make_uint4(0u, 0u, 0u, 0u) : hpk;
                 if (rv) {
                     const size_t so = tokbase + ((size_t)(u0 >> 3) << 8);          // RB32: chunk stride 256 elements
                     *reinterpret_cast<uint4*>(h16 + so) = hpk;
@@ -330,7 +340,18 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                     }
                 }
             }
-            // A[nxt] complete for this thread: make it visible to the async proxy, signal the MMA warp
+            // every pass of this step has been accumulated (each set has seen its last acc_full; MMAs complete in
+            // order), so the A operand may be overwritten: tensor memory -> swizzled smem, then signal the MMA warp
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            tmem_st_wait();
+#pragma unroll
+            for (int pp = 0; pp < FT_NPASS / 2; ++pp) {
+                const int p = 2 * pp + set;
+                const uint4 hv4 = tmem_ld4(tmem_base + ((uint32_t)(q * 32) << 16) + FT_THOLD + p * 8 + hf * 4);
+                tmem_ld_wait();
+                st_shared_v4(smem_u32(sA) + sw128_offset(FT_M, rl, p * FT_PU + hf * 8), hv4);
+            }
+            tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_ready);
@@ -339,7 +360,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                 mbar_wait(&heads_full[step & 1], (step >> 1) & 1);
                 tc_fence_after();
                 float v[4][8];
-                const uint32_t th = tmem_base + ((uint32_t)(q * 32) << 16) + 128 + (step & 1) * 32;
+                const uint32_t th = tmem_base + ((uint32_t)(q * 32) << 16) + FT_THEADS + (step & 1) * 32;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) tmem_ld8(th + 8 * j, v[j]);
                 tmem_ld_wait();
@@ -362,12 +383,12 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 17) tmem_dealloc(tmem_base, 256);
+    if (warp == 17) tmem_dealloc(tmem_base, 512);
 }
 
 static size_t gru_fwd_tc_smem(int X) {
     (void)X;
-    return 2 * FT_ABUF + 2 * FT_AX + FT_NS * FT_BSTAGE + FT_NPASS * 1024 + sizeof(float) * LPG_H + 1024;
+    return FT_ABUF + 2 * FT_AX + FT_NS * FT_BSTAGE + FT_NPASS * 1024 + sizeof(float) * LPG_H + 1024;
 }
 
 extern "C" int toued_gru_forward_tc(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,

@@ -87,6 +87,15 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
                  ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// One lane of a converged warp (elect.sync).  Issuing tcgen05.mma / commit under `if (elect_one())` instead of
+// `if (lane == 0)` lets the compiler prove the branch is taken by exactly one thread and emit the uniform-datapath
+// instructions directly; under a plain lane test it wraps EVERY UTCHMMA in an ELECT / BRA.U.ANY loop (~10 extra
+// instructions per MMA on the single issuing thread -- the bottleneck of a stream of small MMAs).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -115,6 +124,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 // 32 lanes x 4 consecutive columns: thread i of the warp writes row (lane quadrant base + i)
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint4& v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 tmem_ld4(uint32_t taddr) {
+    uint4 r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(taddr));
+    return r;
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
