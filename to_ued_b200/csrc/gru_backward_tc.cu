@@ -118,9 +118,11 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
         }
     } else if (warp == 9) {
         // ===================== MMA issuer =============================================================
-        if (lane == 0) {
+        // The whole warp walks the loop (all lanes wait on the barriers); one elected lane issues (tc.cuh::elect_one).
+        {
             constexpr uint32_t idesc256 = tc_idesc(BT_M, 256, 1), idesc64 = tc_idesc(BT_M, 64, 1);
             const uint32_t a_addr = smem_u32(sA), i_addr = smem_u32(sI);
+            const uint64_t ad0 = tc_smem_desc(a_addr), idd = tc_smem_desc(i_addr);
             uint32_t it = 0;
             uint32_t ait = 0;
             for (int t = 0; t < L; ++t) {
@@ -138,29 +140,32 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                             mbar_wait(&b_full[sg[g]], (it / BT_NSB) & 1);
                         }
                     }
-                    const uint64_t idd = tc_smem_desc(i_addr);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         const int ks = ((kk & 1) << 1) | (kk >> 1);      // 0, 2, 1, 3: the two unit halves progress together
                         mbar_wait(&k_full[ks], ait & 1);
                         tc_fence_after();
-                        if (mma) {
+                        if (mma && elect_one()) {
 #pragma unroll
                             for (int g = 0; g < 3; ++g)
-                                tc_mma(q_addr, tc_smem_desc(a_addr + g * BT_ACHUNK) + 2 * ks,
+                                tc_mma(q_addr, ad0 + (uint64_t)((g * BT_ACHUNK) >> 4) + 2 * ks,
                                        tc_smem_desc(smem_u32(sB + sg[g] * BT_BCHUNK)) + 2 * ks, idesc256, (ub | kk | g) != 0);
                             // z * dh_t (bf16 hi + lo) through the identity: accumulates onto columns [64 ub, 64 ub + 64)
-                            tc_mma(q_addr + ub * 64, tc_smem_desc(a_addr + 3 * BT_ACHUNK) + 2 * ks, idd + 2 * ks, idesc64, 1u);
-                            tc_mma(q_addr + ub * 64, tc_smem_desc(a_addr + 4 * BT_ACHUNK) + 2 * ks, idd + 2 * ks, idesc64, 1u);
+                            tc_mma(q_addr + ub * 64, ad0 + (uint64_t)((3 * BT_ACHUNK) >> 4) + 2 * ks, idd + 2 * ks, idesc64, 1u);
+                            tc_mma(q_addr + ub * 64, ad0 + (uint64_t)((4 * BT_ACHUNK) >> 4) + 2 * ks, idd + 2 * ks, idesc64, 1u);
                         }
+                        __syncwarp();
                     }
-                    if (mma) {
+                    if (elect_one()) {
+                        if (mma) {
 #pragma unroll
-                        for (int g = 0; g < 3; ++g) tc_commit(&b_empty[sg[g]]);
+                            for (int g = 0; g < 3; ++g) tc_commit(&b_empty[sg[g]]);
+                        }
+                        tc_commit(&a_empty);                         // arrival 1 of 2: the MMAs have read the stage
+                        if (mma && ub == 3) tc_commit(&q_full);
                     }
-                    tc_commit(&a_empty);                             // arrival 1 of 2: the MMAs have read the stage
+                    __syncwarp();
                 }
-                if (mma) tc_commit(&q_full);
             }
         }
     } else if (warp == 10) {
