@@ -2,8 +2,9 @@
 //
 // A CTA owns 128 sequences (UMMA_M = 128, cta_group::1) for all L reverse-scan steps.
 //   * hidden state h' lives in shared memory as the fp16 K-major SW128 A operand (4 K-blocks x 16 KB),
-//     single-buffered: the epilogue parks h_t in spare tensor-memory columns during the step and copies it
-//     into the A operand once the step's last MMA has read it (this frees 64 KB for two more B stages);
+//     NOT in shared memory: the hidden state lives in tensor memory (2 x 128 columns, fp16 pairs) and is the
+//     TMEM-resident A operand of the recurrent MMAs -- re-reading a 64 KB A tile from shared memory for each of
+//     the 16 passes of a step was the bound of this kernel (the tensor core fetches smem operands at ~64 B/clk);
 //   * the recurrent matrix is pre-packed once per meta-step into fp16 SW128 "pass" images
 //     (16 passes x [3 gates x 16 units = 48 rows][256 k] = 24 KB each) and streamed from L2 by a
 //     TMA-producer warp (cp.async.bulk + mbarrier, 2 stages);
@@ -34,8 +35,9 @@ constexpr int FT_BX = (FT_XN / 8) * 256;           // 2048 B: input part (no-swi
 constexpr int FT_BSTAGE = FT_BH + FT_BX;           // 26624 B per pass image (multiple of 1024)
 constexpr int FT_AX = (FT_M / 8) * 256;            // 4096 B: x tile of the A operand
 constexpr int FT_ABUF = FT_KB * FT_M * 128;        // 65536 B
-constexpr int FT_NS = 4;                  // B stages
-constexpr int FT_THEADS = 256, FT_TTILE = 320, FT_THOLD = 352;   // tensor-memory columns: 4 x 64 gate accumulators at 0, then these
+constexpr int FT_NS = 6;                  // B stages
+constexpr int FT_THEADS = 128, FT_TTILE = 192, FT_THOLD = 256;   // tensor-memory columns: 2 x 64 gate accumulators at 0, 2 x 32 head
+                                                                 // accumulators, 4 x 8 relu(h) tiles, 2 x 128 columns of hidden state
 constexpr int FT_THREADS = 576;           // 2 sets of 8 epilogue warps (even / odd passes) + producer warp + MMA warp
 
 // Wh[k][c] (fp32, c = g*256 + unit) -> fp16 pass images: image[p][kb][row = g*16 + u][128 B swizzled]
@@ -89,13 +91,12 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
     // (offset arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared
     //  address space and emits LDS / STS instead of generic LD / ST)
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char* sA = smem;                                   // 2 x 64 KB   h' (SW128 K-blocks)
-    unsigned char* sAx = sA + FT_ABUF;                      // 2 x 4 KB    x tile (no-swizzle K = 16 block)
+    unsigned char* sAx = smem;                                  // 2 x 4 KB    x tile (no-swizzle K = 16 block)
     unsigned char* sB = sAx + 2 * FT_AX;                        // FT_NS x 26 KB
     unsigned char* sHB = sB + FT_NS * FT_BSTAGE;                // 16 x 1 KB   head weights [w_pi | W_y] as fp16 hi / lo, per pass
     float* sbhn = reinterpret_cast<float*>(sHB + FT_NPASS * 1024);    // [256]
-    __shared__ __align__(8) uint64_t b_full[FT_NS], b_empty[FT_NS], acc_full[4], acc_empty[4], a_ready;
-    __shared__ __align__(8) uint64_t stage_full[4], stage_empty[4], heads_full[2];
+    __shared__ __align__(8) uint64_t b_full[FT_NS], b_empty[FT_NS], acc_full[2], acc_empty[2], a_ready;
+    __shared__ __align__(8) uint64_t stage_full[4], stage_empty[4], heads_full[2], h0_ready;
     __shared__ uint32_t tmem_base_s;
 
     const LpgOffsets o = lpg_offsets(X);
@@ -104,10 +105,11 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
 
     if (tid == 0) {
         for (int s = 0; s < FT_NS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int a = 0; a < 4; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
         mbar_init(&a_ready, 16);
         for (int a = 0; a < 4; ++a) { mbar_init(&stage_full[a], 8); mbar_init(&stage_empty[a], 1); }
         for (int a = 0; a < 2; ++a) mbar_init(&heads_full[a], 1);
+        mbar_init(&h0_ready, 1);
         mbar_fence_init();
     }
     if (warp == 17) tmem_alloc(&tmem_base_s, 512);     // 2 x 64 gate accumulators + 2 x 32 head accumulators + 4 x 8 relu(h) tiles + 128 columns of parked h_t  (FT_T* below)
@@ -122,7 +124,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
         *reinterpret_cast<__half*>(sHB + p * 1024 + k16_offset(n, k)) = __float2half_rn(n < 16 ? hi : w - hi);
     }
     // initial carry = 0 (both A buffers); x tiles zero, then x_{L-1} into tile 0 (twice: W_i hi / lo parts)
-    for (int i = tid; i < (FT_ABUF + 2 * FT_AX) / 16; i += FT_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < (2 * FT_AX) / 16; i += FT_THREADS) reinterpret_cast<uint4*>(sAx)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     if (tid < FT_M) {
         const int r_ = row0 + tid;
@@ -181,14 +183,13 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                 __syncwarp();
             };
             int cur = 0;
-            const uint32_t a_addr = smem_u32(sA);
             for (int t = L - 1, step = 0; t >= 0; --t, ++step) {
-                if (step > 0) { mbar_wait(&a_ready, (step - 1) & 1); }
+                if (step > 0) { mbar_wait(&a_ready, (step - 1) & 1); } else { mbar_wait(&h0_ready, 0); }
                 tc_fence_after();
                 const uint64_t axd = tc_smem_desc_k16(smem_u32(sAx + cur * FT_AX));
                 for (int p = 0; p < FT_NPASS; ++p, ++it) {
-                    const int s = it % FT_NS, a = it & 3;
-                    mbar_wait(&acc_empty[a], ((it >> 2) & 1) ^ 1);
+                    const int s = it % FT_NS, a = it & 1;
+                    mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
                     mbar_wait(&b_full[s], (it / FT_NS) & 1);
                     tc_fence_after();
                     if (elect_one()) {
@@ -197,13 +198,14 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                         // input projection + bias first: initialises all 64 accumulator columns
                         // (r | z | 0 | i_n); the recurrent part then accumulates onto columns 0..47 (r | z | h_n)
                         tc_mma(d_addr, axd, tc_smem_desc_k16(b_addr + FT_BH), idesc_x, 0u);
-                        const uint64_t ad0 = tc_smem_desc(a_addr), bd0 = tc_smem_desc(b_addr);
+                        const uint64_t bd0 = tc_smem_desc(b_addr);
+                        const uint32_t ha = tmem_base + FT_THOLD + cur * 128;     // h' of this step: 8 columns per K = 16 step
 #pragma unroll
                         for (int kb = 0; kb < FT_KB; ++kb) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks)      // descriptor address field is in 16-byte units
-                                tc_mma(d_addr, ad0 + (uint64_t)((kb * FT_M * 128 + ks * 32) >> 4),
-                                       bd0 + (uint64_t)((kb * FT_PN * 128 + ks * 32) >> 4), idesc, 1u);
+                                tc_mma_ts(d_addr, ha + (kb * 4 + ks) * 8,
+                                          bd0 + (uint64_t)((kb * FT_PN * 128 + ks * 32) >> 4), idesc, 1u);
                         }
                         tc_commit(&b_empty[s]);
                         tc_commit(&acc_full[a]);
@@ -231,6 +233,14 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
         const size_t gs = (size_t)L * R32 * 32 * LPG_H;       // elements per saved factor plane
         const size_t Rp = ((size_t)R + 63) & ~(size_t)63;     // rows padded to the 64-token image blocks
         int cur = 0;
+        // initial carry = 0: hidden-state buffer 0 (this thread's columns)
+#pragma unroll
+        for (int pp = 0; pp < FT_NPASS / 2; ++pp)
+            tmem_st4(tmem_base + ((uint32_t)(q * 32) << 16) + FT_THOLD + (2 * pp + set) * 8 + hf * 4, make_uint4(0u, 0u, 0u, 0u));
+        tmem_st_wait();
+        tc_fence_before();
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (warp == 0 && lane == 0) mbar_arrive(&h0_ready);
         float b_heads[1 + LPG_Y];
         b_heads[0] = lpg[o.b_pi];
 #pragma unroll
@@ -252,12 +262,11 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
             }
             // mask for the NEXT processed step (t-1): its carry is zero where done[t-1]
             const bool zero_next = (t > 0) && done[((size_t)n_ag * L + (t - 1)) * W + w_ag];
-            const unsigned char* Acur = sA;
             const size_t tokbase = rb32_index((size_t)t, R32, rsafe, 0);
             for (int p = set; p < FT_NPASS; p += 2) {
                 const uint32_t it = (uint32_t)step * FT_NPASS + p;
-                const int a = it & 3;                              // accumulators {set, set + 2}: the MMAs run two passes ahead of this set
-                mbar_wait(&acc_full[a], (it >> 2) & 1);
+                const int a = set;
+                mbar_wait(&acc_full[a], (it >> 1) & 1);
                 tc_fence_after();
                 float ar[8], az[8], an[8], ai[8];
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + a * 64 + hf * 8;
@@ -265,13 +274,14 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                 tmem_ld8(ta + FT_PU, az);
                 tmem_ld8(ta + 2 * FT_PU, an);
                 tmem_ld8(ta + 3 * FT_PU, ai);
+                const uint4 hp_tm = tmem_ld4(tmem_base + ((uint32_t)(q * 32) << 16) + FT_THOLD + cur * 128 + p * 8 + hf * 4);   // h' of these units
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[a]);
                 const int u0 = p * FT_PU + hf * 8;              // first of this thread's 8 units
                 const uint32_t soff = sw128_offset(FT_M, rl, u0);
-                const uint4 hp_raw = *reinterpret_cast<const uint4*>(Acur + soff);
+                const uint4 hp_raw = hp_tm;
                 const __half2* hp2 = reinterpret_cast<const __half2*>(&hp_raw);
                 float hp[8];
 #pragma unroll
@@ -306,8 +316,8 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                 {   // relu(h_t) of this pass -> K = 16 tile (8 TMEM columns) for the heads MMA
                     const uint32_t sb = it & 3;
                     mbar_wait(&stage_empty[sb], ((it >> 2) & 1) ^ 1);
-                    // park the (masked) next carry in tensor memory until the A operand may be overwritten
-                    tmem_st4(tmem_base + ((uint32_t)(q * 32) << 16) + FT_THOLD + p * 8 + hf * 4, zero_next ? make_uint4(0u, 0u, 0u, 0u) : hpk);
+                    // the (masked) next carry goes into the other hidden-state buffer of tensor memory
+                    tmem_st4(tmem_base + ((uint32_t)(q * 32) << 16) + FT_THOLD + (cur ^ 1) * 128 + p * 8 + hf * 4, zero_next ? make_uint4(0u, 0u, 0u, 0u) : hpk);
                     uint4 rl4;
                     const __half2 z2 = __float2half2_rn(0.0f);
                     const __half2* hs = reinterpret_cast<const __half2*>(&hpk);
@@ -340,19 +350,9 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                     }
                 }
             }
-            // every pass of this step has been accumulated (each set has seen its last acc_full; MMAs complete in
-            // order), so the A operand may be overwritten: tensor memory -> swizzled smem, then signal the MMA warp
-            asm volatile("bar.sync 1, 512;" ::: "memory");
+            // this warp's part of h_t is in tensor memory: signal the MMA warp (no shared-memory traffic, no proxy fence)
             tmem_st_wait();
-#pragma unroll
-            for (int pp = 0; pp < FT_NPASS / 2; ++pp) {
-                const int p = 2 * pp + set;
-                const uint4 hv4 = tmem_ld4(tmem_base + ((uint32_t)(q * 32) << 16) + FT_THOLD + p * 8 + hf * 4);
-                tmem_ld_wait();
-                st_shared_v4(smem_u32(sA) + sw128_offset(FT_M, rl, p * FT_PU + hf * 8), hv4);
-            }
             tc_fence_before();
-            fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_ready);
             // heads: the 16 heads MMAs of this step are complete -> bias, softmax, outputs (one thread per row)
@@ -388,7 +388,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
 
 static size_t gru_fwd_tc_smem(int X) {
     (void)X;
-    return FT_ABUF + 2 * FT_AX + FT_NS * FT_BSTAGE + FT_NPASS * 1024 + sizeof(float) * LPG_H + 1024;
+    return 2 * FT_AX + FT_NS * FT_BSTAGE + FT_NPASS * 1024 + sizeof(float) * LPG_H + 1024;
 }
 
 extern "C" int toued_gru_forward_tc(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,
