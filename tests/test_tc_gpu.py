@@ -56,8 +56,8 @@ def test_tcgen05_mn_major_gemm_tile(built_lib):
     assert err < 2e-4, f"MN-major tcgen05 tile mismatch: max abs err {err}"
 
 
-@pytest.mark.parametrize("cond", [False, True])
-def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond):
+@pytest.mark.parametrize("cond,n", [(False, 6), (True, 6), (False, 5), (True, 3)])
+def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond, n):
     """Tensor-core GRU forward vs the exact-fp32 SIMT kernel on identical inputs.  Stated tolerance:
     pi_hat / y_hat within 3e-3 of the fp32 kernel relative to max |value| (fp16 operands, hidden state
     quantised to fp16 once per step, 20 recurrent steps)."""
@@ -67,7 +67,7 @@ def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond):
     from oracle import prng
     from to_ued_b200 import _lib
     from to_ued_b200.agents.lpg_agent import Tape
-    n, K = 6, 1
+    K = 1           # n = 5 / 3: 320 / 192 sequences, i.e. a ragged last 128-row tile (64 valid rows)
     c = Case("all_shortlife", n=n, seed=4, cond=cond, table_scale=0.5)
     ag, ro = c.agent_state()
     lpg = torch.from_numpy(c.lpg).cuda()
@@ -125,8 +125,8 @@ def _unpack_tile_img(img_u8, n_tok, C):
     return flat[(off // 2).reshape(-1)].reshape(n_tok, C)
 
 
-@pytest.mark.parametrize("mode,cond", [("all_shortlife", False), ("all_vrandlife", True)])
-def test_meta_gradient_tensor_core_path(built_lib, mode, cond, monkeypatch):
+@pytest.mark.parametrize("mode,cond,n", [("all_shortlife", False, 4), ("all_vrandlife", True, 4), ("all_shortlife", False, 3)])
+def test_meta_gradient_tensor_core_path(built_lib, mode, cond, n, monkeypatch):
     """Full LPG meta-gradient with the tensor-core GRU (fp16 forward, bf16 reverse operands, fp32
     accumulation in TMEM) against the fp64 autograd oracle on the same trajectories.
     Stated tolerance: every parameter block within 2e-2 of the oracle relative to the block's max |g|,
@@ -141,8 +141,8 @@ def test_meta_gradient_tensor_core_path(built_lib, mode, cond, monkeypatch):
     from oracle.agents import AgentTables
     from oracle.meta import lpg_meta_grad_train_step as o_step
     from test_meta_grad_gpu import _run
-    K, n = 5, 4
-    c = Case(mode, n=n, seed=7, cond=cond, table_scale=0.3, lifetimes=[250, 3, 250, 250], steps=[0, 0, 17, 246])
+    K = 5           # n = 3: ragged last tile through the whole tensor-core chain (forward, BPTT, weight gradients)
+    c = Case(mode, n=n, seed=7, cond=cond, table_scale=0.3, lifetimes=[250, 3, 250, 250][:n], steps=[0, 0, 17, 246][:n])
     (new_ts, ag2, vc2, met), ws = _run(c, K)
     assert ws.tape.precision == "tc"
     tape = ws.tape
