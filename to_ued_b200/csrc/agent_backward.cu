@@ -198,7 +198,7 @@ __device__ __forceinline__ void load8(const float* p, float* v) {
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ action,
                       const uint16_t* __restrict__ sorted_tok, const float* __restrict__ pi_hat,
                       const float* __restrict__ y_hat, const float* __restrict__ actor_k,
@@ -207,7 +207,7 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
                       float* lam, float* mu, float* __restrict__ d_pi_hat, float* __restrict__ d_y_hat,
                       int n_agents, int W, int L, int D, float lr_a, float lr_c, float max_norm,
                       float alpha, float b_pent, float b_yent, float b_pl2, float b_yl2, float gscale) {
-    extern __shared__ __align__(16) float rec[];       // [T][14] records | [T][13] run vectors | scan | index
+    extern __shared__ __align__(16) float rec[];       // [T][13] records | [min(T, D)][13] run vectors | scan | index
     __shared__ float red[32];
     __shared__ float s_wlast[13];
     __shared__ int iscan[512];
@@ -225,8 +225,8 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
     const float invT = 1.0f / (float)T;
     const float gna = upd_scal[n * 8 + 0], gnc = upd_scal[n * 8 + 1];
     const bool keep = upd_scal[n * 8 + 2] != 0.0f;
-    float* runv = rec + (size_t)T * 14;
-    float* scan = runv + (size_t)T * 13;
+    float* runv = rec + (size_t)T * 13;
+    float* scan = runv + (size_t)min(T, D) * 13;       // a run is a distinct table row: at most D of them
     const SegIndex si = seg_index_build(scan + 2 * 256 * 13, iscan, st, ob, T);
 
     // ---- A. entropy regularisers evaluated at the UPDATED tables (lpg_agent.py:119-120) -------
@@ -236,7 +236,7 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
     for (int j = 0; j < 13; ++j) last[j] = 0.f;
     for (int tok = tid; tok < T; tok += 256) {
         const TokFwd f = tok_forward(a1, c1, D, ob[tok], act[tok]);
-        float* r = rec + tok * 14;
+        float* r = rec + tok * 13;
         {   // dH/dp_j = -(log(p_j + e) + 1);  dz = p * (dHp - sum p dHp)
             float dh[5], s = 0.f;
 #pragma unroll
@@ -253,14 +253,13 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
 #pragma unroll
             for (int j = 0; j < 8; ++j) r[5 + j] = k * f.y[j] * (dh[j] - s);
         }
-        r[13] = f.tf;
 #pragma unroll
         for (int j = 0; j < 13; ++j) last[j] = fmaf(f.tf, r[j], last[j]);
     }
 #pragma unroll
     for (int j = 0; j < 13; ++j) last[j] = block_sum(last[j], red);
     __syncthreads();
-    seg_reduce<13, 14>(rec, si, T, runv, scan, sflags);
+    seg_reduce<13, 13>(rec, si, T, runv, scan, sflags);
     for (int r = tid; r < si.nruns; r += 256) {
         const int row = si.run_row[r];
         const float* g = runv + r * 13;
@@ -300,9 +299,8 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
         const size_t li = (size_t)t * R + (size_t)n * W + w;
         const TokFwd f = tok_forward(a0, c0, D, ob[tok], act[tok]);
         float yh[8]; load8(y_hat + li * 8, yh);
-        float* r = rec + tok * 14;
+        float* r = rec + tok * 13;
         tok_grad(f, pi_hat[li], yh, invT, alpha, r);
-        r[13] = f.tf;
 #pragma unroll
         for (int j = 0; j < 13; ++j) last[j] = fmaf(f.tf, r[j], last[j]);
     }
@@ -310,7 +308,7 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
     for (int j = 0; j < 13; ++j) last[j] = block_sum(last[j], red);     // g_k[D-1]
     __syncthreads();
     // ---- B2. <g_k, lam>, <g_k^c, mu> ------------------------------------------------------------
-    seg_reduce<13, 14>(rec, si, T, runv, scan, sflags);           // g_k rows
+    seg_reduce<13, 13>(rec, si, T, runv, scan, sflags);           // g_k rows
     float dot_a = 0.f, dot_c = 0.f;
     for (int r = tid; r < si.nruns; r += 256) {
         const int row = si.run_row[r];
@@ -367,7 +365,7 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
         const TokFwd f = tok_forward(a0, c0, D, ob[tok], act[tok]);
         const float ph = pi_hat[li];
         float yh[8]; load8(y_hat + li * 8, yh);
-        float* r = rec + tok * 14;
+        float* r = rec + tok * 13;
         const float* wr = runv + (size_t)si.run[pos] * 13;
         float v[13];
 #pragma unroll
@@ -417,7 +415,7 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
     for (int j = 0; j < 13; ++j) hl[j] = block_sum(hl[j], red);
     __syncthreads();
     // ---- B3c. segmented sums of the HVP contributions into lam_k / mu_k --------------------------
-    seg_reduce<13, 14>(rec, si, T, runv, scan, sflags);
+    seg_reduce<13, 13>(rec, si, T, runv, scan, sflags);
     for (int r = tid; r < si.nruns; r += 256) {
         const int row = si.run_row[r];
         const float* g = runv + r * 13;
@@ -445,7 +443,7 @@ extern "C" int toued_agent_backward(const int32_t* obs, const uint8_t* action, c
                                     float grad_scale, void* stream) {
     const int T = n_workers * rollout_len;
     TOUED_CHECK(n_agents > 0 && T > 0, "toued_agent_backward: empty problem");
-    const size_t smem = sizeof(float) * ((size_t)T * 14 + (size_t)T * 13 + 2 * 256 * 13) + seg_index_bytes(T);
+    const size_t smem = sizeof(float) * ((size_t)T * 13 + (size_t)(T < obs_dim ? T : obs_dim) * 13 + 2 * 256 * 13) + seg_index_bytes(T);
     TOUED_CHECK(smem <= 200 * 1024, "toued_agent_backward: W*L=%d too large for shared memory", T);
     TOUED_CUDA(cudaFuncSetAttribute(agent_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     agent_backward_kernel<<<n_agents, 256, smem, (cudaStream_t)stream>>>(

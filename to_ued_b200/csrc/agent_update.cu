@@ -16,9 +16,9 @@
 #include "segreduce.cuh"
 #include "../../include/toued.h"
 
-constexpr int AU_C = 14;   // per-token record: 5 actor dlogits, 8 critic dlogits, tf
+constexpr int AU_C = 13;   // per-token record: 5 actor dlogits, 8 critic dlogits
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 agent_update_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ action,
                     const uint16_t* __restrict__ sorted_tok, const float* __restrict__ pi_hat,
                     const float* __restrict__ y_hat, const float* __restrict__ actor_in,
@@ -26,13 +26,13 @@ agent_update_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__
                     const LevelRec* __restrict__ levels, int32_t* __restrict__ step,
                     float* __restrict__ scal, int n_agents, int W, int L, int D,
                     float lr_a, float lr_c, float max_norm, float alpha) {
-    extern __shared__ __align__(16) float smc[];          // [T][AU_C] records | [T][13] run sums | scan | index
+    extern __shared__ __align__(16) float smc[];          // [T][AU_C] records | [min(T, D)][13] run sums | scan | index
     __shared__ float red[32];
     __shared__ int iscan[512];
     __shared__ unsigned char sflags[512];
     const int n = blockIdx.x, tid = threadIdx.x, T = W * L, R = n_agents * W;
     float* runv = smc + (size_t)T * AU_C;
-    float* scan = runv + (size_t)T * 13;
+    float* scan = runv + (size_t)min(T, D) * 13;          // a run is a distinct table row: at most D of them
     void* idxmem = scan + 2 * 256 * 13;
     const int32_t* ob = obs + (size_t)n * (L + 1) * W;
     const uint8_t* act = action + (size_t)n * T;
@@ -88,7 +88,6 @@ agent_update_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__
 #pragma unroll
         for (int i = 0; i < 8; ++i) rec[5 + i] = cc * y[i] * (mm[i] - b);
         const float tf = 0.001f * (float)ob_time(o);
-        rec[13] = tf;
 #pragma unroll
         for (int j = 0; j < 13; ++j) last[j] = fmaf(tf, rec[j], last[j]);
         m_kl += kl; m_pi2 = fmaf(ph, ph, m_pi2); m_y2 += y2;
@@ -166,8 +165,9 @@ agent_update_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__
     }
 }
 
-static size_t agent_smem_bytes(int T) {
-    return sizeof(float) * ((size_t)T * AU_C + (size_t)T * 13 + 2 * 256 * 13) + seg_index_bytes(T);
+// 108 KB at T = 1280, D = 101: two CTAs per SM, so the 256 agents of a launch are resident at once
+static size_t agent_smem_bytes(int T, int D) {
+    return sizeof(float) * ((size_t)T * AU_C + (size_t)(T < D ? T : D) * 13 + 2 * 256 * 13) + seg_index_bytes(T);
 }
 
 extern "C" int toued_agent_update(const int32_t* obs, const uint8_t* action, const uint16_t* sorted_tok,
@@ -177,7 +177,7 @@ extern "C" int toued_agent_update(const int32_t* obs, const uint8_t* action, con
                                   int n_workers, int rollout_len, int obs_dim, float lr_actor,
                                   float lr_critic, float max_grad_norm, float agent_target_coeff, void* stream) {
     const int T = n_workers * rollout_len;
-    const size_t smem = agent_smem_bytes(T);
+    const size_t smem = agent_smem_bytes(T, obs_dim);
     TOUED_CHECK(n_agents > 0 && T > 0, "toued_agent_update: empty problem");
     TOUED_CHECK(smem <= 200 * 1024, "toued_agent_update: W*L=%d too large for shared memory", T);
     TOUED_CHECK(actor_in != actor_out && critic_in != critic_out, "toued_agent_update: in-place update not supported");
