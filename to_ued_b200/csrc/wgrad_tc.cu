@@ -68,13 +68,14 @@ wgrad_wh_tc_kernel(const unsigned char* __restrict__ hpimg, const unsigned char*
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
+        {   // all lanes wait, one elected lane issues (tc.cuh::elect_one)
             constexpr uint32_t idesc = tc_idesc_mn(128, 192, 1), idesc_x = tc_idesc_mn(128, 256, 1);
             for (int i = 0; i < nblk; ++i) {
                 const int s = i % WT_NS;
                 mbar_wait(&full[s], (i / WT_NS) & 1);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(smem + s * WT_STAGE);
+                if (elect_one()) {
                 if (!xt) {
                     const uint32_t b0 = a0 + 2 * 8192;
 #pragma unroll
@@ -94,8 +95,11 @@ wgrad_wh_tc_kernel(const unsigned char* __restrict__ hpimg, const unsigned char*
                     }
                 }
                 tc_commit(&empty[s]);
+                }
+                __syncwarp();
             }
-            tc_commit(&done_bar);
+            if (elect_one()) tc_commit(&done_bar);
+            __syncwarp();
         }
     } else {
         // epilogue: TMEM lane = j within the tile
@@ -328,7 +332,7 @@ wgrad_heads_mma_kernel(const __half* __restrict__ h16, const float* __restrict__
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
+        {
             // (kind::f16 needs A and B in the same 16-bit format on this part: fp16 x bf16 traps, so relu(h) is
             //  converted to bf16 by the transform warps)
             constexpr uint32_t idesc = tc_idesc_mn(128, 32, 1);
@@ -337,6 +341,7 @@ wgrad_heads_mma_kernel(const __half* __restrict__ h16, const float* __restrict__
                 mbar_wait(&ready[s], (i / HM_NS) & 1);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(smem + s * HM_STAGE), bb = a0 + HM_A + HM_RAW;
+                if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
                     const uint64_t bd = tc_smem_desc_mn_plain(bb + ks * 256, 128, 512);
@@ -346,8 +351,11 @@ wgrad_heads_mma_kernel(const __half* __restrict__ h16, const float* __restrict__
                                (i | ks) != 0);
                 }
                 tc_commit(&empty[s]);
+                }
+                __syncwarp();
             }
-            tc_commit(&done_bar);
+            if (elect_one()) tc_commit(&done_bar);
+            __syncwarp();
         }
     } else {
         // ---- transform warps (0..3), later the epilogue ----
