@@ -198,7 +198,7 @@ __device__ __forceinline__ void load8(const float* p, float* v) {
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256)
 agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ action,
                       const uint16_t* __restrict__ sorted_tok, const float* __restrict__ pi_hat,
                       const float* __restrict__ y_hat, const float* __restrict__ actor_k,

@@ -18,7 +18,7 @@
 
 constexpr int AU_C = 13;   // per-token record: 5 actor dlogits, 8 critic dlogits
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256)
 agent_update_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ action,
                     const uint16_t* __restrict__ sorted_tok, const float* __restrict__ pi_hat,
                     const float* __restrict__ y_hat, const float* __restrict__ actor_in,
