@@ -69,7 +69,7 @@ wgrad_wh_tc_kernel(const unsigned char* __restrict__ hpimg, const unsigned char*
         }
     } else if (warp == 5) {
         {   // all lanes wait, one elected lane issues (tc.cuh::elect_one)
-            constexpr uint32_t idesc = tc_idesc_mn(128, 192, 1), idesc_x = tc_idesc_mn(128, 256, 1);
+            constexpr uint32_t idesc = tc_idesc_mn(128, 192, 1), idesc_x = tc_idesc_mn(64, 256, 1);   // x tiles: M = 64 (one group, 8 rows used)
             for (int i = 0; i < nblk; ++i) {
                 const int s = i % WT_NS;
                 mbar_wait(&full[s], (i / WT_NS) & 1);
@@ -88,7 +88,7 @@ wgrad_wh_tc_kernel(const unsigned char* __restrict__ hpimg, const unsigned char*
                     const uint32_t b0 = a0 + 8192;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        // LBO = 0: both 64-row halves of the M = 128 operand alias the single x group
+                        // M = 64: the single x group (halves the A fetch of these operand-fetch-bound MMAs)
                         const uint64_t ad = tc_smem_desc_mn(a0 + ks * 2048, 0);
                         tc_mma(tmem_base, ad, tc_smem_desc_mn(b0 + ks * 2048, 8192), idesc_x, (i | ks) != 0);
                         tc_mma(tmem_base + 256, ad, tc_smem_desc_mn(b0 + 4 * 8192 + ks * 2048, 8192), idesc_x, (i | ks) != 0);
