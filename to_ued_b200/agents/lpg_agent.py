@@ -98,6 +98,18 @@ class Tape:
         return Transition(self.obs[r], self.action[r], self.reward[r], self.done[r])
 
 
+_SORT_STREAMS = {}
+
+
+def _sort_stream(cur):
+    """One side stream per chain stream (created on first use)."""
+    key = (cur.device.index, cur.cuda_stream)
+    st = _SORT_STREAMS.get(key)
+    if st is None:
+        st = _SORT_STREAMS[key] = torch.cuda.Stream(device=cur.device)
+    return st
+
+
 def lpg_agent_train_step(k, tape: Tape, levels, step, lpg_params, lifetime_conditioning, agent_target_coeff,
                          lr_actor, lr_critic, max_grad_norm, lpg_stride=0):
     """agents/lpg_agent.py:31-85 for update ``k`` of the tape: reads theta_k / phi_k and the k-th rollout,
@@ -106,7 +118,15 @@ def lpg_agent_train_step(k, tape: Tape, levels, step, lpg_params, lifetime_condi
     s = _lib.stream_ptr()
     p = _lib.ptr
     r, a, t0, t1 = tape.ri(k), tape.ai(k), tape.ti(k), tape.ti(k + 1)
-    _lib.call("toued_sort_tokens", p(tape.obs[r]), p(tape.sorted_tok[r]), N, W, L, s)
+    # the token sort is only needed by the agent update: it runs on a side stream next to the LPG forward
+    cur = torch.cuda.current_stream()
+    side = _sort_stream(cur)
+    ev_roll, ev_sort = torch.cuda.Event(), torch.cuda.Event()
+    ev_roll.record(cur)
+    with torch.cuda.stream(side):
+        side.wait_event(ev_roll)
+        _lib.call("toued_sort_tokens", p(tape.obs[r]), p(tape.sorted_tok[r]), N, W, L, _lib.stream_ptr())
+        ev_sort.record(side)
     tape.step_in[a].copy_(step)
     _lib.call("toued_lpg_prepare", p(tape.obs[r]), p(tape.action[r]), p(tape.reward[r]), p(tape.done[r]),
               p(tape.actor[t0]), p(tape.critic[t0]), p(lpg_params), p(step), p(levels), p(tape.x[a]),
@@ -122,6 +142,7 @@ def lpg_agent_train_step(k, tape: Tape, levels, step, lpg_params, lifetime_condi
                   p(tape.h16[a]), p(tape.fac[a]) if tape.fac is not None else None,
                   p(tape.hpimg[a]) if tape.hpimg is not None else None, p(tape.pi_hat[a]), p(tape.y_hat[a]),
                   N, W, L, int(lifetime_conditioning), s)
+    cur.wait_event(ev_sort)
     _lib.call("toued_agent_update", p(tape.obs[r]), p(tape.action[r]), p(tape.sorted_tok[r]), p(tape.pi_hat[a]),
               p(tape.y_hat[a]), p(tape.actor[t0]), p(tape.critic[t0]), p(tape.actor[t1]), p(tape.critic[t1]),
               p(levels), p(step), p(tape.scalars[a]), N, W, L, D, float(lr_actor), float(lr_critic),

@@ -51,10 +51,13 @@ class MetaGradWorkspace:
         R = N * W
         f32 = torch.float32
         self.tape = Tape(N, W, L, obs_dim, K, device, keep_gates=True)
-        self.d_pi_hat = torch.empty((L, R), dtype=f32, device=device)
-        self.d_y_hat = torch.empty((L, R, 8), dtype=f32, device=device)
+        # cotangent buffers are double-buffered over the update index: the agent adjoint of update k-1 and the
+        # embedding gradient of update k run on side streams next to the tensor-core kernels of update k / k-1
+        self.d_pi_hat2 = [torch.empty((L, R), dtype=f32, device=device) for _ in range(2)]
+        self.d_y_hat2 = [torch.empty((L, R, 8), dtype=f32, device=device) for _ in range(2)]
+        self.dx2 = [torch.empty((L, R, 2), dtype=f32, device=device) for _ in range(2)]
+        self.d_pi_hat, self.d_y_hat, self.dx = self.d_pi_hat2[0], self.d_y_hat2[0], self.dx2[0]
         self.dl = torch.empty((L, R, 8), dtype=f32, device=device)
-        self.dx = torch.empty((L, R, 2), dtype=f32, device=device)
         self.lam = torch.empty((N, obs_dim, 8), dtype=f32, device=device)
         self.mu = torch.empty((N, obs_dim, 8), dtype=f32, device=device)
         self.whT = torch.empty((768, 256), dtype=f32, device=device)
@@ -162,6 +165,10 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     ready.record(main)
     eval_done = [None] * S
     eval_stream = _side_streams(dev, S + 1)[S] if S > 1 else _eval_stream(dev)
+    # per chunk: a stream for the agent adjoints and one for the embedding gradients of the reverse pass
+    pool = _side_streams(dev, 3 * S + 1)
+    ab_streams, em_streams = pool[S + 1:2 * S + 1], pool[2 * S + 1:3 * S + 1]
+    evs = {}
 
     # The host enqueues the chains of a group of S mini-batches round-robin, one agent update at a time (forward:
     # k = 0..K-1, reverse: k = K-1..0), so every stream has work from the start of the step and the chains finish
@@ -243,42 +250,77 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                       p(tape.sorted_tok[K]), p(vparams), p(tape.actor[K]), p(ws.lam), p(ws.mu), p(ws.loss_scal),
                       nb, W, L, D, vparams.shape[-1], float(gamma), float(gae_lambda), float(gscale),
                       int(outer_product_quirk), s)
+            evs[mb] = {"ml": torch.cuda.Event(), "ab": {}, "bwd": {}, "wg": {}, "em": {}}
+            evs[mb]["ml"].record(streams[slot])
+
+    def _agent_backward(ws, tape, k, buf, s):
+        _lib.call("toued_agent_backward", p(tape.obs[k]), p(tape.action[k]), p(tape.sorted_tok[k]),
+                  p(tape.pi_hat[k]), p(tape.y_hat[k]), p(tape.actor[k]), p(tape.critic[k]),
+                  p(tape.actor[k + 1]), p(tape.critic[k + 1]), p(tape.scalars[k]), p(ws.lam), p(ws.mu),
+                  p(ws.d_pi_hat2[buf]), p(ws.d_y_hat2[buf]), nb, W, L, D, float(actor.learning_rate),
+                  float(critic.learning_rate), float(actor.max_grad_norm),
+                  float(lpg_hypers.agent_target_coeff), *[float(b) for b in bK], float(gscale), s)
 
     def backward_step(mb, k):
+        """Reverse pass of update k.  Tensor-core path: three streams per chunk --
+             agent stream : agent adjoint (HVPs through clip/SGD) of update k        -> d pi_hat / d y_hat [k & 1]
+             chain stream : GRU BPTT, weight-gradient GEMMs of update k              (back to back over k)
+             embed stream : embedding-MLP gradient of update k                       (reads dx [k & 1])
+           so the latency-bound per-agent kernels run beside the tensor-core kernels of the neighbouring update
+           instead of between them."""
         slot = mb % S
         ws, tape = wss[slot], wss[slot].tape
+        first = (mb < S and k == K - 1)                 # first use of this workspace's partial buffers
+        if not tc:
+            with torch.cuda.stream(streams[slot]):
+                s = _lib.stream_ptr()
+                _agent_backward(ws, tape, k, 0, s)
+                _lib.call("toued_gru_backward", p(tape.done[k]), p(lpg), p(ws.whT), p(tape.h[k]), p(tape.gates[k]),
+                          p(tape.y_hat[k]), p(ws.d_pi_hat), p(ws.d_y_hat), p(ws.dl), p(ws.dx), nb, W, L, cond, s)
+                _lib.call("toued_lpg_wgrad", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg), p(tape.x[k]),
+                          p(tape.h[k]), p(tape.gates[k]), p(ws.d_pi_hat), p(ws.dl), p(ws.dx), p(ws.partials),
+                          nb, W, L, D, cond, 0 if first else 1, s)
+            return
+        ev, buf = evs[mb], k & 1
+        for d in ("ab", "bwd", "wg", "em"):
+            ev[d][k] = torch.cuda.Event()
+        with torch.cuda.stream(ab_streams[slot]):
+            st = ab_streams[slot]
+            if k == K - 1:
+                st.wait_event(ev["ml"])
+            if k + 2 <= K - 1:
+                st.wait_event(ev["wg"][k + 2])              # the cotangent buffer is free again
+            _agent_backward(ws, tape, k, buf, _lib.stream_ptr())
+            ev["ab"][k].record(st)
         with torch.cuda.stream(streams[slot]):
+            st = streams[slot]
             s = _lib.stream_ptr()
-            # ---- reverse pass, update k ----
-            if True:
-                _lib.call("toued_agent_backward", p(tape.obs[k]), p(tape.action[k]), p(tape.sorted_tok[k]),
-                          p(tape.pi_hat[k]), p(tape.y_hat[k]), p(tape.actor[k]), p(tape.critic[k]),
-                          p(tape.actor[k + 1]), p(tape.critic[k + 1]), p(tape.scalars[k]), p(ws.lam), p(ws.mu),
-                          p(ws.d_pi_hat), p(ws.d_y_hat), nb, W, L, D, float(actor.learning_rate),
-                          float(critic.learning_rate), float(actor.max_grad_norm),
-                          float(lpg_hypers.agent_target_coeff), *[float(b) for b in bK], float(gscale), s)
-                first = (mb < S and k == K - 1)                 # first use of this workspace's partial buffers
-                if tc:
-                    _lib.call("toued_gru_backward_tc", p(tape.done[k]), p(lpg), p(ws.whb_img), p(tape.h16[k]),
-                              p(tape.fac[k]), p(tape.y_hat[k]), p(ws.d_pi_hat), p(ws.d_y_hat), p(ws.dgimg), p(ws.dl),
-                              p(ws.dx), nb, W, L, cond, s)
-                    _lib.call("toued_lpg_wgrad_tc", p(tape.hpimg[k]), p(ws.dgimg), p(tape.ximg[k]), p(tape.h16[k]),
-                              p(ws.d_pi_hat), p(ws.dl), p(ws.partials), p(ws.partials[ws.off_small:]),
-                              nb, W, L, 0 if first else 1, s)
-                    _lib.call("toued_lpg_wgrad_embed", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg),
-                              p(ws.dx), p(ws.partials), nb, W, L, D, cond, 0 if first else 1, s)
-                else:
-                    _lib.call("toued_gru_backward", p(tape.done[k]), p(lpg), p(ws.whT), p(tape.h[k]), p(tape.gates[k]),
-                              p(tape.y_hat[k]), p(ws.d_pi_hat), p(ws.d_y_hat), p(ws.dl), p(ws.dx), nb, W, L, cond, s)
-                    _lib.call("toued_lpg_wgrad", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg), p(tape.x[k]),
-                              p(tape.h[k]), p(tape.gates[k]), p(ws.d_pi_hat), p(ws.dl), p(ws.dx), p(ws.partials),
-                              nb, W, L, D, cond, 0 if first else 1, s)
+            st.wait_event(ev["ab"][k])
+            if k + 2 <= K - 1:
+                st.wait_event(ev["em"][k + 2])              # dx [k & 1] has been consumed
+            _lib.call("toued_gru_backward_tc", p(tape.done[k]), p(lpg), p(ws.whb_img), p(tape.h16[k]),
+                      p(tape.fac[k]), p(tape.y_hat[k]), p(ws.d_pi_hat2[buf]), p(ws.d_y_hat2[buf]), p(ws.dgimg), p(ws.dl),
+                      p(ws.dx2[buf]), nb, W, L, cond, s)
+            ev["bwd"][k].record(st)
+            _lib.call("toued_lpg_wgrad_tc", p(tape.hpimg[k]), p(ws.dgimg), p(tape.ximg[k]), p(tape.h16[k]),
+                      p(ws.d_pi_hat2[buf]), p(ws.dl), p(ws.partials), p(ws.partials[ws.off_small:]),
+                      nb, W, L, 0 if first else 1, s)
+            ev["wg"][k].record(st)
+        with torch.cuda.stream(em_streams[slot]):
+            st = em_streams[slot]
+            st.wait_event(ev["bwd"][k])
+            _lib.call("toued_lpg_wgrad_embed", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg),
+                      p(ws.dx2[buf]), p(ws.partials), nb, W, L, D, cond, 0 if first else 1, _lib.stream_ptr())
+            ev["em"][k].record(st)
 
     def backward_end(mb):
         slot = mb % S
         ws, tape, msum = wss[slot], wss[slot].tape, msums[slot]
         sl, sub2, state, am, levels = ctx.pop(mb)
         with torch.cuda.stream(streams[slot]):
+            ev = evs.pop(mb)
+            if ev["em"]:
+                streams[slot].wait_event(ev["em"][0])          # joins the embed stream (the agent stream is already joined)
             # ---- metrics (sums over agents; divided by n_global after the all-reduce) ----
             lpg_loss, value_loss = ws.loss_scal[:, 0], ws.loss_scal[:, 1]
             reg = (lpg_loss - lpg_hypers.policy_entropy_coeff * am.policy_entropy + lpg_hypers.policy_l2_coeff * am.policy_l2
