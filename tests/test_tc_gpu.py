@@ -125,8 +125,9 @@ def _unpack_tile_img(img_u8, n_tok, C):
     return flat[(off // 2).reshape(-1)].reshape(n_tok, C)
 
 
-@pytest.mark.parametrize("mode,cond,n", [("all_shortlife", False, 4), ("all_vrandlife", True, 4), ("all_shortlife", False, 3)])
-def test_meta_gradient_tensor_core_path(built_lib, mode, cond, n, monkeypatch):
+@pytest.mark.parametrize("mode,cond,n,w", [("all_shortlife", False, 4, 64), ("all_vrandlife", True, 4, 64),
+                                           ("all_shortlife", False, 3, 64), ("all_shortlife", False, 3, 8)])
+def test_meta_gradient_tensor_core_path(built_lib, mode, cond, n, w, monkeypatch):
     """Full LPG meta-gradient with the tensor-core GRU (fp16 forward, bf16 reverse operands, fp32
     accumulation in TMEM) against the fp64 autograd oracle on the same trajectories.
     Stated tolerance: every parameter block within 2e-2 of the oracle relative to the block's max |g|,
@@ -141,8 +142,9 @@ def test_meta_gradient_tensor_core_path(built_lib, mode, cond, n, monkeypatch):
     from oracle.agents import AgentTables
     from oracle.meta import lpg_meta_grad_train_step as o_step
     from test_meta_grad_gpu import _run
-    K = 5           # n = 3: ragged last tile through the whole tensor-core chain (forward, BPTT, weight gradients)
-    c = Case(mode, n=n, seed=7, cond=cond, table_scale=0.3, lifetimes=[250, 3, 250, 250][:n], steps=[0, 0, 17, 246][:n])
+    K = 5           # n = 3: ragged last tile through the whole tensor-core chain (forward, BPTT, weight gradients);
+                    # w = 8: 24 sequences = one partial tile, not a multiple of 32 (streaming head-gradient kernel)
+    c = Case(mode, n=n, w=w, seed=7, cond=cond, table_scale=0.3, lifetimes=[250, 3, 250, 250][:n], steps=[0, 0, 17, 246][:n])
     (new_ts, ag2, vc2, met), ws = _run(c, K)
     assert ws.tape.precision == "tc"
     tape = ws.tape
