@@ -46,12 +46,7 @@ def train_a2c_agent(rng, agent_state: AgentState, rollout_manager, num_train_ste
     scal = torch.empty((N, 4), dtype=f32, device=dev)
     msum = torch.zeros((N, 2), dtype=f32, device=dev)
     levels = agent_state.level.packed
-    rng = np.asarray(rng, np.uint32).reshape(-1, 2)
-    keys = np.empty((K, N, 2), np.uint32)
-    for k in range(K):                                        # a2c.py:95-96
-        ks = prng.split(rng, 2)
-        rng, keys[k] = ks[:, 0, :], ks[:, 1, :]
-    keys_d = torch.from_numpy(keys.view(np.int32)).to(dev, non_blocking=True)
+    keys_d = prng.chain_device(prng.to_device(rng, dev), K)   # a2c.py:95-96, derived on the device
     p, s = _lib.ptr, _lib.stream_ptr()
     for k in range(K):
         i, o = k & 1, (k & 1) ^ 1
