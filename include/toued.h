@@ -227,6 +227,14 @@ int toued_pack_wh_forward(const float* lpg_params, void* wh_img, int lifetime_co
 int toued_gru_forward_tc(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,
                          void* h16, void* fac, void* hpimg, float* pi_hat, float* y_hat, int n_agents,
                          int n_workers, int rollout_len, int lifetime_conditioning, void* stream);
+/* Per-candidate variants for the ES path (meta/train.py:167-176: every agent runs its own LPG parameter vector):
+ * agent n uses lpg_params + n * lpg_stride and the pass images wh_img + n * 425,984 bytes; one CTA per agent
+ * (n_workers <= 128 sequences); inference only (no saved activations).                                   */
+int toued_pack_wh_forward_multi(const float* lpg_params, void* wh_img, int lifetime_conditioning, int n_sets,
+                                int lpg_stride, void* stream);
+int toued_gru_forward_tc_multi(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,
+                               float* pi_hat, float* y_hat, int n_agents, int n_workers, int rollout_len,
+                               int lifetime_conditioning, int lpg_stride, void* stream);
 
 /* Pack Wh into the bf16 SW128 chunk images of the tensor-core reverse pass (384 KiB).               */
 int toued_pack_wh_backward(const float* lpg_params, void* whb_img, void* stream);

@@ -25,3 +25,4 @@ def fp32_gru(monkeypatch):
     """Run the exact-fp32 SIMT GRU kernels (the tight-tolerance parity tests use these)."""
     import to_ued_b200
     monkeypatch.setattr(to_ued_b200, "GRU_PRECISION", "fp32")
+    monkeypatch.setattr(to_ued_b200, "ES_PRECISION", "fp32")

@@ -35,7 +35,7 @@ def test_es_ask_tell_match_oracle(built_lib):
     np.testing.assert_allclose(m.cpu().numpy(), want.m.numpy(), rtol=1e-4, atol=1e-7)
 
 
-def test_lpg_es_train_step_matches_oracle(built_lib):
+def test_lpg_es_train_step_matches_oracle(built_lib, fp32_gru):
     from to_ued_b200.meta.es import lpg_es_train_step, create_es_train_state
     from to_ued_b200.meta.train import LPGTrainState
     from to_ued_b200.models.lpg import LPG
@@ -75,3 +75,35 @@ def test_lpg_es_train_step_matches_oracle(built_lib):
     diff = np.abs(es2.es_state["mean"].cpu().numpy() - want.mean.numpy())
     assert (diff > 5e-6).mean() < 1e-4 and diff.max() < 2e-2
     assert es2.es_state["gen_counter"] == 1 and abs(es2.es_state["lrate"] - 1e-2 * 0.999) < 1e-12
+
+
+def test_es_per_candidate_forward_on_tensor_cores(built_lib, monkeypatch):
+    """TOUED_ES_PRECISION=tc: the per-candidate LPG forward on tcgen05 (one parameter set and one set of pass
+    images per CTA) against the exact-fp32 per-candidate kernel.  Stated tolerance: agent tables after K updates
+    within 5e-3 (relative to max |value|), candidate fitness within 0.15 (fitness comes from sampled rollouts of
+    the trained tables, so it is compared loosely)."""
+    import to_ued_b200
+    from to_ued_b200.agents.lpg_agent import train_lpg_agent
+    n, K = 6, 3
+    c = Case("all_vrandlife", n=n, seed=11, cond=True, table_scale=0.4)
+    rs = np.random.RandomState(5)
+    P = c.lpg.size
+    Pp = (P + 3) // 4 * 4
+    cand = np.zeros((n, Pp), np.float32)
+    cand[:, :P] = c.lpg[None] + 0.05 * rs.randn(n, P).astype(np.float32)
+    cand_d = torch.from_numpy(cand).cuda()
+
+    class _Cand:
+        params = cand_d
+        model = type("M", (), {"lifetime_conditioning": True})()
+    out = {}
+    for prec in ("fp32", "tc"):
+        monkeypatch.setattr(to_ued_b200, "ES_PRECISION", prec)
+        ag, ro = c.agent_state()
+        ag2, _, m = train_lpg_agent(c.keys, _Cand, ag, ro, K, 0.5, lpg_stride=Pp)
+        torch.cuda.synchronize()
+        out[prec] = (ag2.actor_state.params.cpu().numpy(), ag2.critic_state.params.cpu().numpy(), m.policy_entropy.cpu().numpy())
+    for i, name in enumerate(("actor", "critic", "policy_entropy")):
+        e = rel_err(out["tc"][i], out["fp32"][i])
+        print(f"ES tc vs fp32 {name}: rel err {e:.2e}")
+        assert e < 5e-3, (name, e)

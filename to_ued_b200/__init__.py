@@ -5,6 +5,9 @@ import os
 #   "tc"   tcgen05 tensor cores, fp16 operands / fp32 accumulation in TMEM (production path)
 #   "fp32" exact-fp32 SIMT kernels (numerical baseline)
 GRU_PRECISION = os.environ.get("TOUED_GRU_PRECISION", "tc")
+# per-candidate LPG forward of the ES path (meta/es.py): "tc" = tensor-core kernel with one parameter set and one set of
+# pass images per CTA (default, 8x faster), "fp32" = exact SIMT kernel (tight parity tests)
+ES_PRECISION = os.environ.get("TOUED_ES_PRECISION", "tc")
 
 # Number of CUDA streams on which independent mini-batches of agents run concurrently inside one meta-step
 # (only used when num_mini_batches > 1; results are independent of it).

@@ -66,6 +66,8 @@ SIGNATURES = {
     "toued_tc_gemm_mixed_test": [_P] * 5,
     "toued_tc_gemm_mn_test": [_P] * 4 + [_I] * 3 + [_P],
     "toued_pack_wh_forward": [_P, _P, _I, _P],
+    "toued_pack_wh_forward_multi": [_P, _P, _I, _I, _I, _P],
+    "toued_gru_forward_tc_multi": [_P] * 6 + [_I] * 5 + [_P],
     "toued_key_split": [_P, _I, _I, _I, _I, _P, _P],
     "toued_key_chain": [_P, _I, _I, _P, _P, _P],
     "toued_gru_forward_tc": [_P] * 9 + [_I] * 4 + [_P],
@@ -100,7 +102,7 @@ def stream_ptr():
 
 
 # kernels launched by one call of each entry point (for the bench's gpu_launches count)
-KERNELS_PER_CALL = {"toued_lpg_wgrad": 3, "toued_init_tables": 2, "toued_lpg_wgrad_tc": 2, "toued_pack_wh_forward": 2}
+KERNELS_PER_CALL = {"toued_lpg_wgrad": 3, "toued_init_tables": 2, "toued_lpg_wgrad_tc": 2, "toued_pack_wh_forward": 2, "toued_pack_wh_forward_multi": 2}
 LAUNCHES = {}          # entry point -> number of calls since reset_counters()
 PROFILE = None         # when a dict: entry point -> list of (start, end) CUDA events
 

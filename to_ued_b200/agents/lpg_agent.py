@@ -42,7 +42,7 @@ class Tape:
     else, so K can be the full agent lifetime."""
 
     def __init__(self, n_agents, n_workers, rollout_len, obs_dim, num_updates, device, keep_gates=True,
-                 precision=None):
+                 precision=None, per_agent_params=False):
         import to_ued_b200
         N, W, L, D, K = n_agents, n_workers, rollout_len, obs_dim, num_updates
         R, dev = N * W, device
@@ -67,12 +67,13 @@ class Tape:
             f16 = torch.float16
             Rp = (R + 63) // 64 * 64
             R32 = (R + 31) // 32 * 32                         # RB32 layout pads rows to blocks of 32
-            self.h16 = torch.empty((ka, L, R32, 256), dtype=f16, device=dev)
+            self.h16 = None if per_agent_params else torch.empty((ka, L, R32, 256), dtype=f16, device=dev)
             self.fac = torch.empty((ka, 4, L, R32, 256), dtype=f16, device=dev) if self.record else None
             # bf16 token-tile images (rows >= R of a partial 64-token block stay zero)
             self.hpimg = torch.zeros((ka, L * Rp * 256 * 2), dtype=torch.uint8, device=dev) if self.record else None
             self.ximg = torch.zeros((ka, L * Rp * 128), dtype=torch.uint8, device=dev) if self.record else None
-            self.wh_img = torch.zeros(16 * 26624 // 2, dtype=f16, device=dev)      # 16 pass images of 26 KiB
+            # 16 pass images of 26 KiB per LPG parameter set (one set, or one per agent on the ES path)
+            self.wh_img = torch.zeros((N if per_agent_params else 1) * 16 * 26624 // 2, dtype=f16, device=dev)
             self.h = self.gates = None
         else:
             self.h = torch.empty((ka, L, R, 256), dtype=f32, device=dev)
@@ -132,8 +133,12 @@ def lpg_agent_train_step(k, tape: Tape, levels, step, lpg_params, lifetime_condi
               p(tape.actor[t0]), p(tape.critic[t0]), p(lpg_params), p(step), p(levels), p(tape.x[a]),
               p(tape.ximg[a]) if tape.ximg is not None else None,
               N, W, L, D, int(lifetime_conditioning), int(lpg_stride), s)
-    if lpg_stride or tape.precision != "tc":
-        # exact-fp32 kernel (also the per-candidate-parameter path of ES: one CTA per agent)
+    if lpg_stride and tape.precision == "tc":
+        # per-candidate parameters on the tensor cores: one CTA and one set of pass images per agent
+        _lib.call("toued_gru_forward_tc_multi", p(tape.x[a]), p(tape.done[r]), p(lpg_params), p(tape.wh_img),
+                  p(tape.pi_hat[a]), p(tape.y_hat[a]), N, W, L, int(lifetime_conditioning), int(lpg_stride), s)
+    elif lpg_stride or tape.precision != "tc":
+        # exact-fp32 kernel (also the default per-candidate-parameter path of ES: one CTA per agent)
         _lib.call("toued_gru_forward", p(tape.x[a]), p(tape.done[r]), p(lpg_params), p(tape.h[a]),
                   p(tape.gates[a]) if tape.gates is not None else None, p(tape.pi_hat[a]), p(tape.y_hat[a]),
                   N, W, L, int(lifetime_conditioning), int(lpg_stride), s)
@@ -161,7 +166,9 @@ def train_lpg_agent_steps(rng, lpg_train_state, agent_state: AgentState, rollout
     L, K = rollout_manager.train_rollout_len, num_train_steps
     dev = actor.params.device
     if tape is None:
-        tape = Tape(N, W, L, env.obs_dim, K, dev, keep_gates=False, precision="fp32" if lpg_stride else None)
+        import to_ued_b200
+        tape = Tape(N, W, L, env.obs_dim, K, dev, keep_gates=False,
+                    precision=to_ued_b200.ES_PRECISION if lpg_stride else None, per_agent_params=bool(lpg_stride))
     levels = agent_state.level.packed
     step = actor.step.clone()
     state = agent_state.env_state.packed.clone()
@@ -174,6 +181,8 @@ def train_lpg_agent_steps(rng, lpg_train_state, agent_state: AgentState, rollout
     cond = lpg_train_state.model.lifetime_conditioning if hasattr(lpg_train_state, "model") else False
     if tape.precision == "tc" and not lpg_stride:             # recurrent matrix -> fp16 SW128 pass images
         _lib.call("toued_pack_wh_forward", p(lpg), p(tape.wh_img), int(cond), _lib.stream_ptr())
+    elif tape.precision == "tc":                              # ... one set of images per candidate
+        _lib.call("toued_pack_wh_forward_multi", p(lpg), p(tape.wh_img), int(cond), N, int(lpg_stride), _lib.stream_ptr())
     yield
     for k in range(K):
         r = tape.ri(k)

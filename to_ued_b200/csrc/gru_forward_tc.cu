@@ -41,9 +41,11 @@ constexpr int FT_THEADS = 128, FT_TTILE = 192, FT_THOLD = 256;   // tensor-memor
 constexpr int FT_THREADS = 576;           // 2 sets of 8 epilogue warps (even / odd passes) + producer warp + MMA warp
 
 // Wh[k][c] (fp32, c = g*256 + unit) -> fp16 pass images: image[p][kb][row = g*16 + u][128 B swizzled]
-__global__ void pack_wh_fwd_kernel(const float* __restrict__ Wh, __half* __restrict__ img) {
+__global__ void pack_wh_fwd_kernel(const float* __restrict__ Wh, __half* __restrict__ img, size_t lpg_stride) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= LPG_H * LPG_G) return;
+    Wh += (size_t)blockIdx.y * lpg_stride;                       // one parameter set per blockIdx.y
+    img += (size_t)blockIdx.y * (FT_NPASS * FT_BSTAGE / 2);
     const int k = i / LPG_G, c = i % LPG_G;
     const int g = c / LPG_H, unit = c % LPG_H, p = unit / FT_PU, u = unit % FT_PU;
     char* base = reinterpret_cast<char*>(img) + (size_t)p * FT_BSTAGE;
@@ -52,10 +54,12 @@ __global__ void pack_wh_fwd_kernel(const float* __restrict__ Wh, __half* __restr
 
 // input part of the pass images: rows [0,16) Wi_r, [16,32) Wi_z, [32,48) zero, [48,64) Wi_n of the pass's
 // 16 units; k = input index (k < X: Wi[k], k == 7: bias b_i, else 0)
-__global__ void pack_wi_fwd_kernel(const float* __restrict__ lpg, int X, __half* __restrict__ img) {
+__global__ void pack_wi_fwd_kernel(const float* __restrict__ lpg, int X, __half* __restrict__ img, size_t lpg_stride) {
     const LpgOffsets o = lpg_offsets(X);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= FT_NPASS * FT_XN * 16) return;
+    lpg += (size_t)blockIdx.y * lpg_stride;
+    img += (size_t)blockIdx.y * (FT_NPASS * FT_BSTAGE / 2);
     const int k = i & 15, row = (i >> 4) % FT_XN, p = i / (16 * FT_XN);
     const int blk = row >> 4, u = p * FT_PU + (row & 15);
     // k in [8,16) holds the fp16 residual of slot k-8 (the x tile repeats x there): raw step / lifetime
@@ -71,14 +75,26 @@ __global__ void pack_wi_fwd_kernel(const float* __restrict__ lpg, int X, __half*
     *reinterpret_cast<__half*>(base + k16_offset(row, k)) = __float2half_rn(v);
 }
 
-extern "C" int toued_pack_wh_forward(const float* lpg_params, void* wh_img, int lifetime_conditioning, void* stream) {
+static int pack_wh_forward(const float* lpg_params, void* wh_img, int lifetime_conditioning, int n_sets, size_t lpg_stride,
+                           void* stream) {
     const int X = lifetime_conditioning ? 7 : 5;
-    pack_wh_fwd_kernel<<<(LPG_H * LPG_G + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        lpg_params + lpg_offsets(X).Wh, (__half*)wh_img);
+    pack_wh_fwd_kernel<<<dim3((LPG_H * LPG_G + 255) / 256, n_sets), 256, 0, (cudaStream_t)stream>>>(
+        lpg_params + lpg_offsets(X).Wh, (__half*)wh_img, lpg_stride);
     TOUED_LAUNCH_CHECK();
-    pack_wi_fwd_kernel<<<(FT_NPASS * FT_XN * 16 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(lpg_params, X, (__half*)wh_img);
+    pack_wi_fwd_kernel<<<dim3((FT_NPASS * FT_XN * 16 + 255) / 256, n_sets), 256, 0, (cudaStream_t)stream>>>(
+        lpg_params, X, (__half*)wh_img, lpg_stride);
     TOUED_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int toued_pack_wh_forward(const float* lpg_params, void* wh_img, int lifetime_conditioning, void* stream) {
+    return pack_wh_forward(lpg_params, wh_img, lifetime_conditioning, 1, 0, stream);
+}
+
+extern "C" int toued_pack_wh_forward_multi(const float* lpg_params, void* wh_img, int lifetime_conditioning, int n_sets,
+                                           int lpg_stride, void* stream) {
+    TOUED_CHECK(n_sets > 0 && lpg_stride > 0, "toued_pack_wh_forward_multi: bad arguments");
+    return pack_wh_forward(lpg_params, wh_img, lifetime_conditioning, n_sets, (size_t)lpg_stride, stream);
 }
 
 template <int X>
@@ -86,7 +102,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
 gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ done,
                       const float* __restrict__ lpg, const __half* __restrict__ wh_img,
                       __half* __restrict__ h16, __half* __restrict__ fac, unsigned char* __restrict__ hpimg,
-                      float* __restrict__ pi_hat, float* __restrict__ y_hat, int R, int L, int W) {
+                      float* __restrict__ pi_hat, float* __restrict__ y_hat, int R, int L, int W,
+                      int rows_per_cta, size_t lpg_stride) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // (offset arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared
     //  address space and emits LDS / STS instead of generic LD / ST)
@@ -101,7 +118,11 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
 
     const LpgOffsets o = lpg_offsets(X);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row0 = blockIdx.x * FT_M;
+    // rows_per_cta = 128: shared parameters, dense 128-row tiles.  rows_per_cta = W (<= 128) with lpg_stride != 0: one
+    // agent and one parameter set (own pass images) per CTA -- the per-candidate forward of the ES path.
+    const int row0 = blockIdx.x * rows_per_cta;
+    lpg += (size_t)blockIdx.x * lpg_stride;
+    if (lpg_stride) wh_img += (size_t)blockIdx.x * (FT_NPASS * FT_BSTAGE / 2);
 
     if (tid == 0) {
         for (int s = 0; s < FT_NS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
@@ -128,7 +149,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
     __syncthreads();
     if (tid < FT_M) {
         const int r_ = row0 + tid;
-        if (r_ < R) {
+        if (tid < rows_per_cta && r_ < R) {
             const float4* xp = reinterpret_cast<const float4*>(x + ((size_t)(L - 1) * R + r_) * LPG_XP);
             const float4 x0 = xp[0], x1 = xp[1];
             __half2 h0 = __floats2half2_rn(x0.x, x0.y), h1 = __floats2half2_rn(x0.z, x0.w);
@@ -226,7 +247,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
         const int set = warp >> 3, q = warp & 3, hf = (warp >> 2) & 1;
         const int rl = q * 32 + lane;                 // row within the tile == TMEM lane
         const int row = row0 + rl;
-        const bool rv = row < R;
+        const bool rv = rl < rows_per_cta && row < R;
         const int rsafe = rv ? row : 0;
         const int n_ag = rsafe / W, w_ag = rsafe % W;
         const size_t R32 = ((size_t)R + 31) >> 5;             // 32-row blocks of the RB32 layout
@@ -332,7 +353,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                 }
                 if (rv) {
                     const size_t so = tokbase + ((size_t)(u0 >> 3) << 8);          // RB32: chunk stride 256 elements
-                    *reinterpret_cast<uint4*>(h16 + so) = hpk;
+                    if (h16) *reinterpret_cast<uint4*>(h16 + so) = hpk;
                     if (fac) {
                         // the reverse pass rebuilds its factors from the gates (and h' from h16 of step t+1)
                         *reinterpret_cast<uint4*>(fac + so) = pack8(rr);
@@ -391,24 +412,44 @@ static size_t gru_fwd_tc_smem(int X) {
     return 2 * FT_AX + FT_NS * FT_BSTAGE + FT_NPASS * 1024 + sizeof(float) * LPG_H + 1024;
 }
 
-extern "C" int toued_gru_forward_tc(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,
-                                    void* h16, void* fac, void* hpimg, float* pi_hat, float* y_hat, int n_agents,
-                                    int n_workers, int rollout_len, int lifetime_conditioning, void* stream) {
+static int gru_forward_tc_launch(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,
+                                 void* h16, void* fac, void* hpimg, float* pi_hat, float* y_hat, int n_agents,
+                                 int n_workers, int rollout_len, int lifetime_conditioning, size_t lpg_stride, void* stream) {
     const int R = n_agents * n_workers;
-    TOUED_CHECK(R > 0 && rollout_len > 0, "toued_gru_forward_tc: empty problem");
-    const int blocks = (R + FT_M - 1) / FT_M;
+    const int rows = lpg_stride ? n_workers : FT_M;
+    const int blocks = lpg_stride ? n_agents : (R + FT_M - 1) / FT_M;
     cudaStream_t st = (cudaStream_t)stream;
     if (lifetime_conditioning) {
         const size_t smem = gru_fwd_tc_smem(7);
         TOUED_CUDA(cudaFuncSetAttribute(gru_forward_tc_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gru_forward_tc_kernel<7><<<blocks, FT_THREADS, smem, st>>>(x, done, lpg_params, (const __half*)wh_img, (__half*)h16,
-                                                                    (__half*)fac, (unsigned char*)hpimg, pi_hat, y_hat, R, rollout_len, n_workers);
+                                                                    (__half*)fac, (unsigned char*)hpimg, pi_hat, y_hat, R, rollout_len, n_workers,
+                                                                    rows, lpg_stride);
     } else {
         const size_t smem = gru_fwd_tc_smem(5);
         TOUED_CUDA(cudaFuncSetAttribute(gru_forward_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gru_forward_tc_kernel<5><<<blocks, FT_THREADS, smem, st>>>(x, done, lpg_params, (const __half*)wh_img, (__half*)h16,
-                                                                    (__half*)fac, (unsigned char*)hpimg, pi_hat, y_hat, R, rollout_len, n_workers);
+                                                                    (__half*)fac, (unsigned char*)hpimg, pi_hat, y_hat, R, rollout_len, n_workers,
+                                                                    rows, lpg_stride);
     }
     TOUED_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int toued_gru_forward_tc(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,
+                                    void* h16, void* fac, void* hpimg, float* pi_hat, float* y_hat, int n_agents,
+                                    int n_workers, int rollout_len, int lifetime_conditioning, void* stream) {
+    TOUED_CHECK(n_agents * n_workers > 0 && rollout_len > 0, "toued_gru_forward_tc: empty problem");
+    TOUED_CHECK(h16 != nullptr, "toued_gru_forward_tc: h16 is required");
+    return gru_forward_tc_launch(x, done, lpg_params, wh_img, h16, fac, hpimg, pi_hat, y_hat, n_agents, n_workers, rollout_len,
+                                 lifetime_conditioning, 0, stream);
+}
+
+extern "C" int toued_gru_forward_tc_multi(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,
+                                          float* pi_hat, float* y_hat, int n_agents, int n_workers, int rollout_len,
+                                          int lifetime_conditioning, int lpg_stride, void* stream) {
+    TOUED_CHECK(n_agents > 0 && n_workers > 0 && rollout_len > 0, "toued_gru_forward_tc_multi: empty problem");
+    TOUED_CHECK(n_workers <= FT_M && lpg_stride > 0, "toued_gru_forward_tc_multi: n_workers=%d must be <= 128 and lpg_stride > 0", n_workers);
+    return gru_forward_tc_launch(x, done, lpg_params, wh_img, nullptr, nullptr, nullptr, pi_hat, y_hat, n_agents, n_workers,
+                                 rollout_len, lifetime_conditioning, (size_t)lpg_stride, stream);
 }
