@@ -189,6 +189,10 @@ int toued_init_tables(const uint32_t* keys, const uint8_t* mask, float* tables, 
 int toued_masked_reset(const void* levels, const uint8_t* mask, int32_t* state, int32_t* obs,
                        int32_t* step, int n_agents, int n_workers, int max_grid_size, void* stream);
 
+/* Host helper (plain C loop, no GPU): out u32[n_keys][n] = threefry_2x32(keys[i], iota(n)), jax 0.4.13 rule
+ * (jax/_src/prng.py threefry_random_bits): the host-side level generator / level sampler key plumbing.   */
+int toued_host_iota_bits(const uint32_t* keys, int n_keys, int n, uint32_t* out);
+
 /* ---- key derivation on the device (jax 0.4.13 threefry2x32 split, bit-exact) ---------------------- */
 
 /* out u32[n_keys][count][2] = jax.random.split(keys_in[i], num)[offset : offset + count]

@@ -68,6 +68,7 @@ SIGNATURES = {
     "toued_pack_wh_forward": [_P, _P, _I, _P],
     "toued_pack_wh_forward_multi": [_P, _P, _I, _I, _I, _P],
     "toued_gru_forward_tc_multi": [_P] * 6 + [_I] * 5 + [_P],
+    "toued_host_iota_bits": [_P, _I, _I, _P],
     "toued_key_split": [_P, _I, _I, _I, _I, _P, _P],
     "toued_key_chain": [_P, _I, _I, _P, _P, _P],
     "toued_gru_forward_tc": [_P] * 9 + [_I] * 4 + [_P],

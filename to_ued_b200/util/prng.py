@@ -34,9 +34,30 @@ def PRNGKey(seed: int) -> np.ndarray:
     return np.array([seed >> 32, seed & 0xFFFFFFFF], np.uint32)
 
 
+_NATIVE = [None]
+
+
+def _native_iota_bits():
+    """toued_host_iota_bits of libtoued.so (a plain C loop on the host), or False if the library is not built."""
+    if _NATIVE[0] is None:
+        try:
+            from .. import _lib
+            _NATIVE[0] = _lib.lib().toued_host_iota_bits
+        except Exception:
+            _NATIVE[0] = False
+    return _NATIVE[0]
+
+
 def iota_bits(key, n: int) -> np.ndarray:
     """threefry_2x32(key, iota(n)): uint32[..., 2] -> uint32[..., n]"""
     key = np.asarray(key, np.uint32)
+    fn = _native_iota_bits() if key.size >= 8 else False          # batched keys: native host loop
+    if fn:
+        k2 = np.ascontiguousarray(key.reshape(-1, 2))
+        out = np.empty((k2.shape[0], n), np.uint32)
+        if fn(k2.ctypes.data, k2.shape[0], int(n), out.ctypes.data) != 0:
+            raise RuntimeError("toued_host_iota_bits failed")
+        return out.reshape(key.shape[:-1] + (n,))
     m = n + (n & 1)
     c = np.arange(m, dtype=np.uint32)
     if n & 1:
