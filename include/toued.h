@@ -161,6 +161,17 @@ int toued_a2c_update(const int32_t* obs, const uint8_t* action, const float* rew
                      float lr_actor, float lr_critic, float max_grad_norm, float gamma, float gae_lambda,
                      float entropy_coeff, int outer_product_quirk, void* stream);
 
+/* agents/a2c.py:79-125, the whole training loop in one call: num_updates x [toued_rollout -> toued_sort_tokens ->
+ * toued_a2c_update], tables ping-ponging between (actor0, critic0) and (actor1, critic1) -- the result is in buffer
+ * (num_updates & 1); keys u32[num_updates][N][2] (toued_key_chain); loss_sums f32[N][2] += {actor_loss, critic_loss}
+ * of every update.  Keeps the 2500-update lifetime of the algorithmic-regret antagonist off the Python interpreter.  */
+int toued_a2c_train(const void* levels, const uint32_t* keys, float* actor0, float* actor1, float* critic0,
+                    float* critic1, int32_t* state, int32_t* obs, uint8_t* action, float* reward, uint8_t* done,
+                    uint16_t* sorted_tok, int32_t* step, float* scalars, float* loss_sums, int num_updates,
+                    int n_agents, int n_workers, int rollout_len, int obs_dim, int max_grid_size, int max_n_objs,
+                    float lr_actor, float lr_critic, float max_grad_norm, float gamma, float gae_lambda,
+                    float entropy_coeff, int outer_product_quirk, void* stream);
+
 /* ---- OpenES ask / tell (evosax==0.1.4, meta/train.py:133-227) ----------------------------------- */
 /* candidates f32[popsize][cand_stride] (first P of each row used; cand_stride a multiple of 4 floats so
  * every candidate is 16-byte aligned) in pair-adjacent order (2i = mean + sigma z_i, 2i+1 = mean - sigma z_i). */

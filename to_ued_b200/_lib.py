@@ -60,6 +60,7 @@ SIGNATURES = {
     "toued_es_ask": [_P, _P, _F, _P, _I, _I, _I, _P],
     "toued_es_tell": [_P] * 5 + [_I, _I, _I] + [_F] * 5 + [_I, _F, _P],
     "toued_a2c_update": [_P] * 12 + [_I] * 4 + [_F] * 6 + [_I, _P],
+    "toued_a2c_train": [_P] * 15 + [_I] * 7 + [_F] * 6 + [_I, _P],
     "toued_init_tables": [_P] * 3 + [_I] * 3 + [_P],
     "toued_masked_reset": [_P] * 5 + [_I] * 3 + [_P],
     "toued_tc_gemm_test": [_P] * 5,

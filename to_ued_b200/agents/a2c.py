@@ -48,7 +48,13 @@ def train_a2c_agent(rng, agent_state: AgentState, rollout_manager, num_train_ste
     levels = agent_state.level.packed
     keys_d = prng.chain_device(prng.to_device(rng, dev), K)   # a2c.py:95-96, derived on the device
     p, s = _lib.ptr, _lib.stream_ptr()
-    for k in range(K):
+    if record is None:
+        # the whole lifetime in one native call (a Python loop of 3 launches per update is host-bound)
+        _lib.call("toued_a2c_train", p(levels), p(keys_d), p(a[0]), p(a[1]), p(c[0]), p(c[1]), p(state), p(obs), p(act),
+                  p(rew), p(don), p(st), p(step), p(scal), p(msum), K, N, W, L, D, env.max_grid_size, env.max_n_objs,
+                  float(actor.learning_rate), float(critic.learning_rate), float(actor.max_grad_norm),
+                  float(hypers.gamma), float(hypers.gae_lambda), float(hypers.entropy_coeff), int(outer_product_quirk), s)
+    for k in range(K if record is not None else 0):
         i, o = k & 1, (k & 1) ^ 1
         _lib.call("toued_rollout", p(levels), p(keys_d[k]), p(a[i]), None, p(state), p(obs), p(act), p(rew), p(don),
                   None, N, W, L, D, env.max_grid_size, env.max_n_objs, 0, s)

@@ -172,3 +172,39 @@ extern "C" int toued_a2c_update(const int32_t* obs, const uint8_t* action, const
     TOUED_LAUNCH_CHECK();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// agents/a2c.py:79-125 as ONE call: the whole lifetime of an A2C agent (num_updates x [rollout -> token sort ->
+// A2C update], tables ping-ponging between two buffers) is enqueued from native code.  The antagonist of the
+// algorithmic-regret score trains for up to 2500 updates (mazes); launched from Python the loop is host-bound
+// (~90 us per update in ctypes + tensor bookkeeping against ~25 us of kernels).
+__global__ void a2c_accumulate_kernel(const float* __restrict__ scal, float* __restrict__ sums, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { sums[2 * i] += scal[4 * i]; sums[2 * i + 1] += scal[4 * i + 1]; }
+}
+
+extern "C" int toued_a2c_train(const void* levels, const uint32_t* keys, float* actor0, float* actor1, float* critic0,
+                               float* critic1, int32_t* state, int32_t* obs, uint8_t* action, float* reward,
+                               uint8_t* done, uint16_t* sorted_tok, int32_t* step, float* scalars, float* loss_sums,
+                               int num_updates, int n_agents, int n_workers, int rollout_len, int obs_dim,
+                               int max_grid_size, int max_n_objs, float lr_actor, float lr_critic, float max_grad_norm,
+                               float gamma, float gae_lambda, float entropy_coeff, int outer_product_quirk, void* stream) {
+    TOUED_CHECK(num_updates >= 0 && n_agents > 0, "toued_a2c_train: bad arguments");
+    float* a[2] = {actor0, actor1};
+    float* c[2] = {critic0, critic1};
+    for (int k = 0; k < num_updates; ++k) {
+        const int i = k & 1, o = i ^ 1;
+        int rc = toued_rollout(levels, keys + (size_t)k * n_agents * 2, a[i], nullptr, state, obs, action, reward, done, nullptr,
+                               n_agents, n_workers, rollout_len, obs_dim, max_grid_size, max_n_objs, 0, stream);
+        if (rc) return rc;
+        rc = toued_sort_tokens(obs, sorted_tok, n_agents, n_workers, rollout_len, stream);
+        if (rc) return rc;
+        rc = toued_a2c_update(obs, action, reward, done, sorted_tok, a[i], c[i], a[o], c[o], levels, step, scalars, n_agents,
+                              n_workers, rollout_len, obs_dim, lr_actor, lr_critic, max_grad_norm, gamma, gae_lambda,
+                              entropy_coeff, outer_product_quirk, stream);
+        if (rc) return rc;
+        a2c_accumulate_kernel<<<(n_agents + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scalars, loss_sums, n_agents);
+        TOUED_LAUNCH_CHECK();
+    }
+    return 0;
+}

@@ -53,11 +53,15 @@ def make_train(args):
 
 
 def run_training_experiment(args):
-    if args.log:
-        print("[to_ued_b200] --log: WandB logging is out of scope on this build; metrics are printed instead")
+    if args.log:                                     # train_do.py:89-95 (local run directory instead of WandB)
+        from to_ued_b200.experiments.logging import init_logger
+        print(f"[to_ued_b200] --log: run directory {init_logger(args)}")
     metrics, train_state, level_buffer = make_train(args)(prng.PRNGKey(args.seed))
     torch.cuda.synchronize()
     print([{k: (v if isinstance(v, dict) else float(v)) for k, v in m.items() if not k.startswith("_")} for m in metrics])
+    if args.log:
+        from to_ued_b200.experiments.logging import log_results
+        print("[to_ued_b200] checkpoints:", log_results(args, metrics, train_state, level_buffer))
     return metrics, train_state, level_buffer
 
 
