@@ -166,8 +166,9 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     eval_done = [None] * S
     eval_stream = _side_streams(dev, S + 1)[S] if S > 1 else _eval_stream(dev)
     # per chunk: a stream for the agent adjoints and one for the embedding gradients of the reverse pass
-    pool = _side_streams(dev, 3 * S + 1)
+    pool = _side_streams(dev, 4 * S + 1)
     ab_streams, em_streams = pool[S + 1:2 * S + 1], pool[2 * S + 1:3 * S + 1]
+    ev_streams = [eval_stream] + pool[3 * S + 1:4 * S]          # one evaluation stream per chunk
     evs = {}
 
     # The host enqueues the chains of a group of S mini-batches round-robin, one agent update at a time (forward:
@@ -231,11 +232,11 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
             #      kernel (max_rollout_len sequential steps): it runs on its own stream next to the reverse pass.
             fwd_done = torch.cuda.Event()
             fwd_done.record(streams[slot])
-            with torch.cuda.stream(eval_stream):
-                eval_stream.wait_event(fwd_done)
+            with torch.cuda.stream(ev_streams[slot]):
+                ev_streams[slot].wait_event(fwd_done)
                 returns[sl] = eval_agent(r_evalagent[sl], rollout_manager, levels, tape.actor[K], eval_workers)
                 eval_done[slot] = torch.cuda.Event()
-                eval_done[slot].record(eval_stream)
+                eval_done[slot].record(ev_streams[slot])
             ctx[mb] = (sl, sub2, state, am, levels)
 
     def backward_begin(mb):
@@ -350,7 +351,7 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                 backward_step(mb, k)
         for mb in group:
             backward_end(mb)
-    for st in ([] if S == 1 else list(streams)) + [eval_stream]:
+    for st in ([] if S == 1 else list(streams)) + ev_streams:
         ev = torch.cuda.Event()
         ev.record(st)
         main.wait_event(ev)
