@@ -206,7 +206,6 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
         const int n_ag = rsafe / W, w_ag = rsafe % W;
         const size_t R32 = ((size_t)R + 31) >> 5;
         const size_t gs = (size_t)L * R32 * 32 * LPG_H;
-        const size_t Rp = ((size_t)R + 63) & ~(size_t)63;
         uint32_t ait = 0;
         const uint32_t sA_u32 = smem_u32(sA);
         // ---- software pipeline: the factor loads of the next 8-unit chunk and the head cotangents of the

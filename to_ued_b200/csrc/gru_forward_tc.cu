@@ -34,7 +34,6 @@ constexpr int FT_XN = 64;                          // x-part rows: Wi_r, Wi_z, 0
 constexpr int FT_BX = (FT_XN / 8) * 256;           // 2048 B: input part (no-swizzle K=16 block: x[0..7] incl. the bias 1)
 constexpr int FT_BSTAGE = FT_BH + FT_BX;           // 26624 B per pass image (multiple of 1024)
 constexpr int FT_AX = (FT_M / 8) * 256;            // 4096 B: x tile of the A operand
-constexpr int FT_ABUF = FT_KB * FT_M * 128;        // 65536 B
 constexpr int FT_NS = 6;                  // B stages
 constexpr int FT_THEADS = 128, FT_TTILE = 192, FT_THOLD = 256;   // tensor-memory columns: 2 x 64 gate accumulators at 0, 2 x 32 head
                                                                  // accumulators, 4 x 8 relu(h) tiles, 2 x 128 columns of hidden state
@@ -133,7 +132,7 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
         mbar_init(&h0_ready, 1);
         mbar_fence_init();
     }
-    if (warp == 17) tmem_alloc(&tmem_base_s, 512);     // 2 x 64 gate accumulators + 2 x 32 head accumulators + 4 x 8 relu(h) tiles + 128 columns of parked h_t  (FT_T* below)
+    if (warp == 17) tmem_alloc(&tmem_base_s, 512);     // column map: FT_THEADS / FT_TTILE / FT_THOLD above
 
     for (int i = tid; i < LPG_H; i += FT_THREADS) sbhn[i] = lpg[o.bhn + i];
     // head weights as the B operand of the heads MMA: per pass a [32 n][16 k] no-swizzle block; n < 16: fp16 of
@@ -301,7 +300,6 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[a]);
                 const int u0 = p * FT_PU + hf * 8;              // first of this thread's 8 units
-                const uint32_t soff = sw128_offset(FT_M, rl, u0);
                 const uint4 hp_raw = hp_tm;
                 const __half2* hp2 = reinterpret_cast<const __half2*>(&hp_raw);
                 float hp[8];

@@ -460,7 +460,6 @@ wgrad_heads_mma_kernel(const __half* __restrict__ h16, const float* __restrict__
 }
 
 constexpr int WT_SPLITS = 24;              // 6 tile types x 24 = 144 CTAs
-constexpr int SMT_SPLITS = 592;
 
 extern "C" int toued_wgrad_tc_splits(void) { return WT_SPLITS; }
 
