@@ -35,8 +35,21 @@ def _np(x):
     return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
 
 
-def _floats(m):
-    return {k: (_floats(v) if isinstance(v, dict) else float(v)) for k, v in m.items() if not k.startswith("_")}
+def to_host(m):
+    """Metrics tree -> plain Python (floats / lists), dropping private ``_``-keys; one value at a time (this is the
+    logging path, not the step)."""
+    if isinstance(m, dict):
+        return {k: to_host(v) for k, v in m.items() if not str(k).startswith("_")}
+    if isinstance(m, torch.Tensor):
+        m = m.detach().cpu().numpy()
+    if isinstance(m, np.ndarray):
+        return float(m) if m.size == 1 else m.astype(float).tolist()
+    if isinstance(m, (np.floating, np.integer)):
+        return m.item()
+    return m
+
+
+_floats = to_host
 
 
 def _train_state_arrays(train_state) -> dict:

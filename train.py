@@ -76,7 +76,8 @@ def _shard(agents, vcs, rank, n_local):
 
 
 def _to_float(m):
-    return {k: (_to_float(v) if isinstance(v, dict) else float(v)) for k, v in m.items()}
+    from to_ued_b200.experiments.logging import to_host
+    return to_host(m)
 
 
 def run_training_experiment(args):

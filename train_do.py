@@ -58,7 +58,8 @@ def run_training_experiment(args):
         print(f"[to_ued_b200] --log: run directory {init_logger(args)}")
     metrics, train_state, level_buffer = make_train(args)(prng.PRNGKey(args.seed))
     torch.cuda.synchronize()
-    print([{k: (v if isinstance(v, dict) else float(v)) for k, v in m.items() if not k.startswith("_")} for m in metrics])
+    from to_ued_b200.experiments.logging import to_host
+    print([to_host(m) for m in metrics])
     if args.log:
         from to_ued_b200.experiments.logging import log_results
         print("[to_ued_b200] checkpoints:", log_results(args, metrics, train_state, level_buffer))
