@@ -93,3 +93,17 @@ def test_log_writes_checkpoints_and_restore_resumes_bitwise(built_lib, tmp_path,
     s2 = back.tx.update_(p2, g, {**back.opt_state, "mu": back.opt_state["mu"].clone(), "nu": back.opt_state["nu"].clone()})
     torch.cuda.synchronize()
     assert torch.equal(p1, p2) and s1["count"] == s2["count"] == 4
+
+
+def test_cli_entry_points_print_metrics(built_lib, capsys):
+    """train.py / train_do.py main(): the printed metric trees (ES metrics hold nested dicts of device scalars)."""
+    import train
+    import train_do
+    train.main(["--env_mode", "debug", "--num_agents", "4", "--num_mini_batches", "1", "--train_steps", "1",
+                "--num_agent_updates", "2", "--use_es", "--lifetime_conditioning"])
+    out = capsys.readouterr().out
+    assert "'fitness': {'mean':" in out and "tensor(" not in out
+    train_do.main(["--env_mode", "debug", "--num_agents", "2", "--num_mini_batches", "1", "--buffer_size", "3", "-br", "2",
+                   "--train_steps", "1", "--num_agent_updates", "2", "--score_function", "alg_regret"])
+    out = capsys.readouterr().out
+    assert "'eval_regret':" in out and "tensor(" not in out
