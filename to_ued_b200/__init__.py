@@ -12,3 +12,6 @@ ES_PRECISION = os.environ.get("TOUED_ES_PRECISION", "tc")
 # Number of CUDA streams on which independent mini-batches of agents run concurrently inside one meta-step
 # (only used when num_mini_batches > 1; results are independent of it).
 NUM_STREAMS = int(os.environ.get("TOUED_NUM_STREAMS", "4"))
+# False: every kernel of a chunk runs on the chunk's own stream (no side streams for the token sort, the agent adjoint,
+# the embedding gradient and eval_agent) -- used by bench.py's per-kernel timing pass so that no launch has a neighbour
+SIDE_STREAMS = os.environ.get("TOUED_SIDE_STREAMS", "1") != "0"

@@ -120,8 +120,9 @@ def lpg_agent_train_step(k, tape: Tape, levels, step, lpg_params, lifetime_condi
     p = _lib.ptr
     r, a, t0, t1 = tape.ri(k), tape.ai(k), tape.ti(k), tape.ti(k + 1)
     # the token sort is only needed by the agent update: it runs on a side stream next to the LPG forward
+    import to_ued_b200
     cur = torch.cuda.current_stream()
-    side = _sort_stream(cur)
+    side = _sort_stream(cur) if to_ued_b200.SIDE_STREAMS else cur
     ev_roll, ev_sort = torch.cuda.Event(), torch.cuda.Event()
     ev_roll.record(cur)
     with torch.cuda.stream(side):

@@ -169,6 +169,8 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     pool = _side_streams(dev, 4 * S + 1)
     ab_streams, em_streams = pool[S + 1:2 * S + 1], pool[2 * S + 1:3 * S + 1]
     ev_streams = [eval_stream] + pool[3 * S + 1:4 * S]          # one evaluation stream per chunk
+    if not to_ued_b200.SIDE_STREAMS:                            # per-kernel timing mode: everything on the chunk's stream
+        ab_streams = em_streams = ev_streams = list(streams)
     evs = {}
 
     # The host enqueues the chains of a group of S mini-batches round-robin, one agent update at a time (forward:
