@@ -187,12 +187,6 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                 streams[slot].wait_event(ready)
             if eval_done[slot] is not None:           # the previous chunk on this workspace is still being evaluated
                 streams[slot].wait_event(eval_done[slot])
-            s = _lib.stream_ptr()
-            if mb < S:
-                if tc:
-                    _lib.call("toued_pack_wh_backward", p(lpg), p(ws.whb_img), s)
-                else:
-                    _lib.call("toued_transpose_wh", p(lpg), p(ws.whT), s)
             sl = slice(mb * nb, (mb + 1) * nb)
             sub = AgentState(actor.replace(params=actor.params[sl], step=actor.step[sl]),
                              critic.replace(params=critic.params[sl], step=critic.step[sl]),
@@ -247,6 +241,11 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
         sl = ctx[mb][0]
         with torch.cuda.stream(streams[slot]):
             s = _lib.stream_ptr()
+            if mb < S:                                  # recurrent matrix in the reverse pass's operand layout
+                if tc:
+                    _lib.call("toued_pack_wh_backward", p(lpg), p(ws.whb_img), s)
+                else:
+                    _lib.call("toued_transpose_wh", p(lpg), p(ws.whT), s)
             # ---- value "update" (Q2) + advantage + LPG loss + lam_K (meta/train.py:60-100) ----
             vparams = value_critic_states.params[sl]
             _lib.call("toued_meta_loss", p(tape.obs[K]), p(tape.action[K]), p(tape.reward[K]), p(tape.done[K]),
@@ -339,9 +338,10 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
 
     for g0 in range(0, num_mini_batches, S):
         group = range(g0, min(num_mini_batches, g0 + S))
-        for mb in group:
-            forward_begin(mb)
-        for k in range(K):
+        for mb in group:                                 # first update right behind each chunk's set-up: the GPU
+            forward_begin(mb)                            # gets its first rollout as early as possible
+            forward_step(mb)
+        for k in range(1, K):
             for mb in group:
                 forward_step(mb)
         for mb in group:
