@@ -15,3 +15,6 @@ NUM_STREAMS = int(os.environ.get("TOUED_NUM_STREAMS", "4"))
 # False: every kernel of a chunk runs on the chunk's own stream (no side streams for the token sort, the agent adjoint,
 # the embedding gradient and eval_agent) -- used by bench.py's per-kernel timing pass so that no launch has a neighbour
 SIDE_STREAMS = os.environ.get("TOUED_SIDE_STREAMS", "1") != "0"
+# When a list: the meta-gradient step appends (label, chunk, timing-enabled CUDA event) at its phase boundaries
+# (tools/phase_timeline.py); None in production.
+PHASE_EVENTS = None

@@ -163,6 +163,13 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     returns = torch.empty(N, dtype=torch.float32, device=dev)
     ready = torch.cuda.Event()
     ready.record(main)
+
+    def _phase(label, chunk, stream):                            # tools/phase_timeline.py; no-op in production
+        if to_ued_b200.PHASE_EVENTS is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            to_ued_b200.PHASE_EVENTS.append((label, chunk, e))
+    _phase("start", -1, main)
     eval_done = [None] * S
     eval_stream = _side_streams(dev, S + 1)[S] if S > 1 else _eval_stream(dev)
     # per chunk: a stream for the agent adjoints and one for the embedding gradients of the reverse pass
@@ -204,6 +211,7 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                 next(gens[mb][0])
             except StopIteration as fin:
                 gens[mb] = (fin.value,) + gens[mb][1:]
+            _phase("update", mb, streams[mb % S])
 
     def forward_end(mb):
         slot = mb % S
@@ -228,6 +236,7 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
             #      kernel (max_rollout_len sequential steps): it runs on its own stream next to the reverse pass.
             fwd_done = torch.cuda.Event()
             fwd_done.record(streams[slot])
+            _phase("forward", mb, streams[slot])
             with torch.cuda.stream(ev_streams[slot]):
                 ev_streams[slot].wait_event(fwd_done)
                 returns[sl] = eval_agent(r_evalagent[sl], rollout_manager, levels, tape.actor[K], eval_workers)
@@ -304,10 +313,12 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                       p(tape.fac[k]), p(tape.y_hat[k]), p(ws.d_pi_hat2[buf]), p(ws.d_y_hat2[buf]), p(ws.dgimg), p(ws.dl),
                       p(ws.dx2[buf]), nb, W, L, cond, s)
             ev["bwd"][k].record(st)
+            _phase(f"bwd{k}", mb, st)
             _lib.call("toued_lpg_wgrad_tc", p(tape.hpimg[k]), p(ws.dgimg), p(tape.ximg[k]), p(tape.h16[k]),
                       p(ws.d_pi_hat2[buf]), p(ws.dl), p(ws.partials), p(ws.partials[ws.off_small:]),
                       nb, W, L, 0 if first else 1, s)
             ev["wg"][k].record(st)
+            _phase(f"wgrad{k}", mb, st)
         with torch.cuda.stream(em_streams[slot]):
             st = em_streams[slot]
             st.wait_event(ev["bwd"][k])
@@ -335,6 +346,7 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
             new_step[sl] = sub2.actor_state.step
             new_state[sl] = state
             new_obs[sl] = tape.obs[K][:, -1]
+            _phase("reverse_end", mb, streams[slot])
 
     for g0 in range(0, num_mini_batches, S):
         group = range(g0, min(num_mini_batches, g0 + S))
@@ -393,6 +405,7 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     }
     if return_grad:
         metrics["_grad"] = grad
+    _phase("end", -1, main)
     return new_lpg, agent_out, value_out, metrics
 
 
