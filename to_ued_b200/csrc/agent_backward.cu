@@ -198,16 +198,16 @@ __device__ __forceinline__ void load8(const float* p, float* v) {
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ action,
                       const uint16_t* __restrict__ sorted_tok, const float* __restrict__ pi_hat,
                       const float* __restrict__ y_hat, const float* __restrict__ actor_k,
                       const float* __restrict__ critic_k, const float* __restrict__ actor_k1,
                       const float* __restrict__ critic_k1, const float* __restrict__ upd_scal,
                       float* lam, float* mu, float* __restrict__ d_pi_hat, float* __restrict__ d_y_hat,
-                      int n_agents, int W, int L, int D, float lr_a, float lr_c, float max_norm,
+                      float* run_scratch, int n_agents, int W, int L, int D, float lr_a, float lr_c, float max_norm,
                       float alpha, float b_pent, float b_yent, float b_pl2, float b_yl2, float gscale) {
-    extern __shared__ __align__(16) float rec[];       // [T][13] records | [min(T, D)][13] run vectors | scan | index
+    extern __shared__ __align__(16) float rec[];       // [T][13] records | scan | index   (106 KB at T = 1280: two CTAs per SM)
     __shared__ float red[32];
     __shared__ float s_wlast[13];
     __shared__ int iscan[512];
@@ -225,8 +225,10 @@ agent_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
     const float invT = 1.0f / (float)T;
     const float gna = upd_scal[n * 8 + 0], gnc = upd_scal[n * 8 + 1];
     const bool keep = upd_scal[n * 8 + 2] != 0.0f;
-    float* runv = rec + (size_t)T * 13;
-    float* scan = runv + (size_t)min(T, D) * 13;       // a run is a distinct table row: at most D of them
+    // run vectors [min(T, D)][13] (a run is a distinct table row: at most D of them) live in an L2-resident global
+    // scratch: written once per run, read once per run / token
+    float* runv = run_scratch + (size_t)n * min(T, D) * 13;
+    float* scan = rec + (size_t)T * 13;
     const SegIndex si = seg_index_build(scan + 2 * 256 * 13, iscan, st, ob, T);
 
     // ---- A. entropy regularisers evaluated at the UPDATED tables (lpg_agent.py:119-120) -------
@@ -443,13 +445,19 @@ extern "C" int toued_agent_backward(const int32_t* obs, const uint8_t* action, c
                                     float grad_scale, void* stream) {
     const int T = n_workers * rollout_len;
     TOUED_CHECK(n_agents > 0 && T > 0, "toued_agent_backward: empty problem");
-    const size_t smem = sizeof(float) * ((size_t)T * 13 + (size_t)(T < obs_dim ? T : obs_dim) * 13 + 2 * 256 * 13) + seg_index_bytes(T);
+    const size_t smem = sizeof(float) * ((size_t)T * 13 + 2 * 256 * 13) + seg_index_bytes(T);
     TOUED_CHECK(smem <= 200 * 1024, "toued_agent_backward: W*L=%d too large for shared memory", T);
     TOUED_CUDA(cudaFuncSetAttribute(agent_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    agent_backward_kernel<<<n_agents, 256, smem, (cudaStream_t)stream>>>(
+    TOUED_CUDA(cudaFuncSetAttribute(agent_backward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    cudaStream_t st = (cudaStream_t)stream;
+    float* run_scratch = nullptr;                       // stream-ordered: safe with concurrent chunks on other streams
+    if (int rc = toued_scratch_alloc((void**)&run_scratch, sizeof(float) * 13 * (size_t)(T < obs_dim ? T : obs_dim) * n_agents, st)) return rc;
+    agent_backward_kernel<<<n_agents, 256, smem, st>>>(
         obs, action, sorted_tok, pi_hat, y_hat, actor_k, critic_k, actor_k1, critic_k1, update_scalars, lam, mu,
-        d_pi_hat, d_y_hat, n_agents, n_workers, rollout_len, obs_dim, lr_actor, lr_critic, max_grad_norm,
+        d_pi_hat, d_y_hat, run_scratch, n_agents, n_workers, rollout_len, obs_dim, lr_actor, lr_critic, max_grad_norm,
         agent_target_coeff, policy_entropy_coeff, target_entropy_coeff, policy_l2_coeff, target_l2_coeff, grad_scale);
-    TOUED_LAUNCH_CHECK();
+    const cudaError_t launch_err = cudaGetLastError();
+    if (int rc = toued_scratch_free(run_scratch, st)) return rc;
+    TOUED_CUDA(launch_err);
     return 0;
 }

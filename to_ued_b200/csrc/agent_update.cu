@@ -18,21 +18,22 @@
 
 constexpr int AU_C = 13;   // per-token record: 5 actor dlogits, 8 critic dlogits
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 agent_update_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ action,
                     const uint16_t* __restrict__ sorted_tok, const float* __restrict__ pi_hat,
                     const float* __restrict__ y_hat, const float* __restrict__ actor_in,
                     const float* __restrict__ critic_in, float* actor_out, float* critic_out,
                     const LevelRec* __restrict__ levels, int32_t* __restrict__ step,
-                    float* __restrict__ scal, int n_agents, int W, int L, int D,
+                    float* __restrict__ scal, float* run_scratch, int n_agents, int W, int L, int D,
                     float lr_a, float lr_c, float max_norm, float alpha) {
-    extern __shared__ __align__(16) float smc[];          // [T][AU_C] records | [min(T, D)][13] run sums | scan | index
+    extern __shared__ __align__(16) float smc[];          // [T][AU_C] records | scan | index   (106 KB at T = 1280: two CTAs per SM)
     __shared__ float red[32];
     __shared__ int iscan[512];
     __shared__ unsigned char sflags[512];
     const int n = blockIdx.x, tid = threadIdx.x, T = W * L, R = n_agents * W;
-    float* runv = smc + (size_t)T * AU_C;
-    float* scan = runv + (size_t)min(T, D) * 13;          // a run is a distinct table row: at most D of them
+    // run sums [min(T, D)][13] (a run is a distinct table row: at most D of them): L2-resident global scratch
+    float* runv = run_scratch + (size_t)n * min(T, D) * 13;
+    float* scan = smc + (size_t)T * AU_C;
     void* idxmem = scan + 2 * 256 * 13;
     const int32_t* ob = obs + (size_t)n * (L + 1) * W;
     const uint8_t* act = action + (size_t)n * T;
@@ -167,7 +168,7 @@ agent_update_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__
 
 // 108 KB at T = 1280, D = 101: two CTAs per SM, so the 256 agents of a launch are resident at once
 static size_t agent_smem_bytes(int T, int D) {
-    return sizeof(float) * ((size_t)T * AU_C + (size_t)(T < D ? T : D) * 13 + 2 * 256 * 13) + seg_index_bytes(T);
+    return sizeof(float) * ((size_t)T * AU_C + 2 * 256 * 13) + seg_index_bytes(T);
 }
 
 extern "C" int toued_agent_update(const int32_t* obs, const uint8_t* action, const uint16_t* sorted_tok,
@@ -182,10 +183,16 @@ extern "C" int toued_agent_update(const int32_t* obs, const uint8_t* action, con
     TOUED_CHECK(smem <= 200 * 1024, "toued_agent_update: W*L=%d too large for shared memory", T);
     TOUED_CHECK(actor_in != actor_out && critic_in != critic_out, "toued_agent_update: in-place update not supported");
     TOUED_CUDA(cudaFuncSetAttribute(agent_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    agent_update_kernel<<<n_agents, 256, smem, (cudaStream_t)stream>>>(
+    TOUED_CUDA(cudaFuncSetAttribute(agent_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    cudaStream_t st = (cudaStream_t)stream;
+    float* run_scratch = nullptr;                       // stream-ordered: safe with concurrent chunks on other streams
+    if (int rc = toued_scratch_alloc((void**)&run_scratch, sizeof(float) * 13 * (size_t)(T < obs_dim ? T : obs_dim) * n_agents, st)) return rc;
+    agent_update_kernel<<<n_agents, 256, smem, st>>>(
         obs, action, sorted_tok, pi_hat, y_hat, actor_in, critic_in, actor_out, critic_out,
-        (const LevelRec*)levels, step, scalars, n_agents, n_workers, rollout_len, obs_dim,
+        (const LevelRec*)levels, step, scalars, run_scratch, n_agents, n_workers, rollout_len, obs_dim,
         lr_actor, lr_critic, max_grad_norm, agent_target_coeff);
-    TOUED_LAUNCH_CHECK();
+    const cudaError_t launch_err = cudaGetLastError();
+    if (int rc = toued_scratch_free(run_scratch, st)) return rc;
+    TOUED_CUDA(launch_err);
     return 0;
 }
