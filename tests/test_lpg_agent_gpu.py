@@ -83,3 +83,19 @@ def test_sort_tokens_is_stable_row_sort(built_lib):
     rows = (traj.obs[:, :c.L].reshape(4, T) & 0xFFFF).cpu().numpy()
     want = np.argsort(rows, axis=1, kind="stable")
     np.testing.assert_array_equal(out.cpu().numpy().astype(np.int64), want)
+
+
+@pytest.mark.parametrize("w,L", [(8, 5), (64, 6), (64, 8), (64, 16), (64, 20), (128, 25), (128, 32)])
+def test_sort_tokens_all_sizes(built_lib, w, L):
+    """every variant of the sort (shared-memory network below 512 keys; 2 / 4 / 8 / 16 keys per thread above) against
+    numpy's stable argsort, on random rows with many repeats"""
+    from to_ued_b200 import _lib
+    g = np.random.default_rng(w * 100 + L)
+    n, T = 5, w * L
+    rows = g.integers(0, 40 if T < 1000 else 3201, size=(n, L + 1, w)).astype(np.int32)
+    times = g.integers(0, 50, size=(n, L + 1, w)).astype(np.int32)
+    obs = torch.from_numpy(rows | (times << 16)).cuda()
+    out = torch.full((n, T), -1, dtype=torch.int16, device="cuda")
+    _lib.call("toued_sort_tokens", _lib.ptr(obs), _lib.ptr(out), n, w, L, _lib.stream_ptr())
+    want = np.argsort(rows[:, :L].reshape(n, T), axis=1, kind="stable")
+    np.testing.assert_array_equal(out.cpu().numpy().astype(np.int64), want)

@@ -15,13 +15,78 @@
 #include "../../include/toued.h"
 
 // ------------------------------------------------------------------------------------------------
-// token sort: key = row << 12 | token  (token = t*W + w < 4096), bitonic sort in shared memory
+// token sort: key = row << 12 | token  (token = t*W + w < 4096; keys are unique, so the order is that of a stable
+// sort by row).  Bitonic network over P2 = 256 * E keys, thread t holding keys [t*E, (t+1)*E) in registers:
+// exchange distances below E stay in registers, distances below 32 E go through warp shuffles, and only the few
+// cross-warp distances go through shared memory (6 of the 66 stages at P2 = 2048).
+template <int E>
+__device__ __forceinline__ void sort_cmpx(uint32_t& mine, uint32_t other, bool keep_min) {
+    const uint32_t lo = min(mine, other), hi = max(mine, other);
+    mine = keep_min ? lo : hi;
+}
+
+template <int E>
+__global__ void __launch_bounds__(256)
+sort_tokens_reg_kernel(const int32_t* __restrict__ obs, uint16_t* __restrict__ sorted_tok, int W, int L, int T) {
+    constexpr int P2 = 256 * E;
+    __shared__ uint32_t xch[P2];
+    const int n = blockIdx.x, tid = threadIdx.x, base = tid * E;
+    const int32_t* ob = obs + (size_t)n * (L + 1) * W;      // [L+1][W]; token (t,w) -> ob[t*W+w]
+    uint32_t v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = base + e;
+        v[e] = i < T ? ((uint32_t)ob_idx(ob[i]) << 12) | (uint32_t)i : 0xFFFFFFFFu;
+    }
+    for (int k = 2; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j >= 32 * E; j >>= 1) {         // partner in another warp: through shared memory
+#pragma unroll
+            for (int e = 0; e < E; ++e) xch[base + e] = v[e];
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int i = base + e;
+                sort_cmpx<E>(v[e], xch[i ^ j], ((i & j) == 0) == ((i & k) == 0));
+            }
+            __syncthreads();
+        }
+        for (int j = min(k >> 1, 16 * E); j >= E; j >>= 1) {    // partner in another lane of this warp
+            const int lane_mask = j / E;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int i = base + e;
+                const uint32_t other = __shfl_xor_sync(0xffffffffu, v[e], lane_mask);
+                sort_cmpx<E>(v[e], other, ((i & j) == 0) == ((i & k) == 0));
+            }
+        }
+#pragma unroll
+        for (int j = E / 2; j > 0; j >>= 1) {                   // partner in this thread's registers
+            if (j < k) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    if ((e & j) == 0) {
+                        const bool up = ((base + e) & k) == 0;
+                        const uint32_t a = v[e], b = v[e | j];
+                        const uint32_t lo = min(a, b), hi = max(a, b);
+                        v[e] = up ? lo : hi;
+                        v[e | j] = up ? hi : lo;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if (base + e < T) sorted_tok[(size_t)n * T + base + e] = (uint16_t)(v[e] & 0xFFFu);
+}
+
+// small problems (P2 < 512): plain shared-memory bitonic network
 __global__ void __launch_bounds__(256)
 sort_tokens_kernel(const int32_t* __restrict__ obs, uint16_t* __restrict__ sorted_tok,
                    int W, int L, int T, int P2) {
     extern __shared__ uint32_t keys[];
     const int n = blockIdx.x;
-    const int32_t* ob = obs + (size_t)n * (L + 1) * W;      // [L+1][W]; token (t,w) -> ob[t*W+w]
+    const int32_t* ob = obs + (size_t)n * (L + 1) * W;
     for (int i = threadIdx.x; i < P2; i += blockDim.x)
         keys[i] = i < T ? ((uint32_t)ob_idx(ob[i]) << 12) | (uint32_t)i : 0xFFFFFFFFu;
     __syncthreads();
@@ -47,8 +112,14 @@ extern "C" int toued_sort_tokens(const int32_t* obs, uint16_t* sorted_tok, int n
     const int T = n_workers * rollout_len;
     TOUED_CHECK(T > 0 && T <= 4096, "toued_sort_tokens: W*L=%d must be in 1..4096", T);
     int P2 = 1; while (P2 < T) P2 <<= 1;
-    sort_tokens_kernel<<<n_agents, 256, P2 * sizeof(uint32_t), (cudaStream_t)stream>>>(
-        obs, sorted_tok, n_workers, rollout_len, T, P2);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (P2) {
+        case 512:  sort_tokens_reg_kernel<2><<<n_agents, 256, 0, st>>>(obs, sorted_tok, n_workers, rollout_len, T); break;
+        case 1024: sort_tokens_reg_kernel<4><<<n_agents, 256, 0, st>>>(obs, sorted_tok, n_workers, rollout_len, T); break;
+        case 2048: sort_tokens_reg_kernel<8><<<n_agents, 256, 0, st>>>(obs, sorted_tok, n_workers, rollout_len, T); break;
+        case 4096: sort_tokens_reg_kernel<16><<<n_agents, 256, 0, st>>>(obs, sorted_tok, n_workers, rollout_len, T); break;
+        default:   sort_tokens_kernel<<<n_agents, 256, P2 * sizeof(uint32_t), st>>>(obs, sorted_tok, n_workers, rollout_len, T, P2);
+    }
     TOUED_LAUNCH_CHECK();
     return 0;
 }
