@@ -126,20 +126,29 @@ extern "C" int toued_sort_tokens(const int32_t* obs, uint16_t* sorted_tok, int n
 
 // ------------------------------------------------------------------------------------------------
 // LPG inputs.  One thread per token (n, t, w).
-__device__ __forceinline__ float embed_mlp(const float (&y)[LPG_Y], const float* __restrict__ sp) {
-    // sp: e_w0[Y][E] e_b0[E] e_w1[E] e_b1[1] in shared memory
-    float out = sp[LPG_Y * LPG_E + LPG_E + LPG_E];
-#pragma unroll
+// both applications of the embedding MLP (y_t and y_{t+1}) in one pass over the weights: every weight is read once
+// and nothing has to stay in registers between the two (a two-call version keeps all 161 weights live: 198 registers,
+// one CTA per SM).  Per output the operation order is that of a single application.
+__device__ __forceinline__ void embed_mlp2(const float (&y0)[LPG_Y], const float (&y1)[LPG_Y],
+                                           const float* __restrict__ sp, float& out0, float& out1) {
+    // sp: e_w0[Y][E] e_b0[E] e_w1[E] e_b1[1]
+    out0 = out1 = sp[LPG_Y * LPG_E + LPG_E + LPG_E];
+#pragma unroll 4
     for (int e = 0; e < LPG_E; ++e) {
-        float a = sp[LPG_Y * LPG_E + e];
+        float a0 = sp[LPG_Y * LPG_E + e], a1 = a0;
 #pragma unroll
-        for (int i = 0; i < LPG_Y; ++i) a = fmaf(y[i], sp[i * LPG_E + e], a);
-        out = fmaf(fmaxf(a, 0.0f), sp[LPG_Y * LPG_E + LPG_E + e], out);
+        for (int i = 0; i < LPG_Y; ++i) {
+            const float wgt = sp[i * LPG_E + e];
+            a0 = fmaf(y0[i], wgt, a0);
+            a1 = fmaf(y1[i], wgt, a1);
+        }
+        const float w1 = sp[LPG_Y * LPG_E + LPG_E + e];
+        out0 = fmaf(fmaxf(a0, 0.0f), w1, out0);
+        out1 = fmaf(fmaxf(a1, 0.0f), w1, out1);
     }
-    return out;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 lpg_prepare_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ action,
                    const float* __restrict__ reward, const uint8_t* __restrict__ done,
                    const float* __restrict__ actor, const float* __restrict__ critic,
@@ -176,8 +185,9 @@ lpg_prepare_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ 
     tab_logits8<LPG_Y>(ct, D, ob1, zy);
     softmax_c<LPG_Y>(zy, y1);
     const float d = done[g] ? 1.0f : 0.0f;
-    const float pyt = embed_mlp(y0, sp);
-    const float pyt1 = embed_mlp(y1, sp) * (1.0f - d);              // lpg.py:69
+    float pyt, pyt1;
+    embed_mlp2(y0, y1, sp, pyt, pyt1);
+    pyt1 *= (1.0f - d);                                             // lpg.py:69
     const size_t row = (size_t)n * W + w;
     float4* xo = reinterpret_cast<float4*>(x + ((size_t)t * n_agents * W + row) * LPG_XP);
     xo[0] = make_float4(reward[g], d, pa + 1e-8f, pyt);             // lpg_agent.py:41-43 (pi + 1e-8)
