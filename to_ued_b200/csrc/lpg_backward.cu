@@ -354,24 +354,35 @@ wgrad_small_kernel(const float* __restrict__ x, const float* __restrict__ h, con
 // embedding MLP backward: pyt = MLP(y_t), pyt1 = MLP(y_{t+1}) * (1 - d)   (lpg.py:66-69)
 // per split partial layout = the parameter order e_w0[8][16] e_b0[16] e_w1[16] e_b1[1]  (161 floats)
 constexpr int EM_TOTAL = LPG_Y * LPG_E + 2 * LPG_E + 1;
-__global__ void __launch_bounds__(256)
+constexpr int EM_SREC = 44;            // y[8] | da[16] | relu(a) dp [16] | dp | pad 3: 176 B, float4 rows conflict-free
+__global__ void __launch_bounds__(256, 2)
 embed_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ done,
                       const float* __restrict__ critic, const float* __restrict__ lpg, int emb_off,
                       const float* __restrict__ dx, float* __restrict__ partial, int n_agents, int W, int L, int D,
                       int accumulate) {
-    // phase 1: each thread back-propagates its token through the two embedding-MLP applications and leaves
-    //          (y[8], da[16], relu(a)*dp [16], dp) in shared memory; phase 2: thread o < 161 owns one parameter
-    //          and sums its products over the block's 2 x 256 samples (fixed order -> deterministic).
-    constexpr int SREC = LPG_Y + 2 * LPG_E + 1;            // 41 floats per sample
+    // phase 1: each thread back-propagates its token through the two embedding-MLP applications (one pass over the
+    //          weights for both) and leaves (y[8], da[16], relu(a)*dp [16], dp) per application in shared memory;
+    // phase 2: the block's 2 x 256 samples are split over 4 pairs of warps; in a pair, 32 threads own a 1 x 4 block of
+    //          e_w0 each (one scalar + one float4 load per sample and 4 FMAs), 4 threads a quad of e_b0, 4 a quad of
+    //          e_w1 and one e_b1.  Sums stay in registers over the whole kernel; the 4 pair partials are combined in a
+    //          fixed order at the end (deterministic).
     __shared__ float sp[EM_TOTAL];
-    extern __shared__ __align__(16) float srec[];          // [2 * 256][41] = 82 KB (dynamic)
+    __shared__ float part[4][EM_TOTAL + 3];
+    extern __shared__ __align__(16) float srec[];          // [2 * 256][44] = 88 KB (dynamic)
     const int tid = threadIdx.x;
     for (int i = tid; i < EM_TOTAL; i += 256) sp[i] = lpg[emb_off + i];
     __syncthreads();
     const size_t total = (size_t)n_agents * L * W;
     const size_t R = (size_t)n_agents * W;
     const size_t iters = (total + (size_t)gridDim.x * 256 - 1) / ((size_t)gridDim.x * 256);
-    float acc = 0.0f;                                      // this thread's parameter (tid < 161)
+    const int grp = tid >> 6, lt = tid & 63;               // pair of warps, thread within the pair
+    // role of this thread in phase 2: src = float4 offset inside a record, ysrc = scalar multiplier offset (-1: 1.0)
+    int src = -1, ysrc = -1, out0 = 0, nout = 0;
+    if (lt < 32)      { ysrc = lt >> 2; src = 8 + 4 * (lt & 3); out0 = (lt >> 2) * LPG_E + 4 * (lt & 3); nout = 4; }
+    else if (lt < 36) { src = 8 + 4 * (lt - 32); out0 = LPG_Y * LPG_E + 4 * (lt - 32); nout = 4; }
+    else if (lt < 40) { src = 8 + LPG_E + 4 * (lt - 36); out0 = LPG_Y * LPG_E + LPG_E + 4 * (lt - 36); nout = 4; }
+    else if (lt == 40) { src = 8 + 2 * LPG_E; out0 = LPG_Y * LPG_E + 2 * LPG_E; nout = 1; }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (size_t it = 0; it < iters; ++it) {
         const size_t g = (it * gridDim.x + blockIdx.x) * 256 + tid;
         const bool ok = g < total;
@@ -392,41 +403,61 @@ embed_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
             dp[0] = d.x;
             dp[1] = done[g] ? 0.0f : d.y;
         }
+        float* r0 = srec + (size_t)tid * EM_SREC;
+        float* r1 = srec + (size_t)(256 + tid) * EM_SREC;
+        reinterpret_cast<float4*>(r0)[0] = make_float4(y[0][0], y[0][1], y[0][2], y[0][3]);
+        reinterpret_cast<float4*>(r0)[1] = make_float4(y[0][4], y[0][5], y[0][6], y[0][7]);
+        reinterpret_cast<float4*>(r1)[0] = make_float4(y[1][0], y[1][1], y[1][2], y[1][3]);
+        reinterpret_cast<float4*>(r1)[1] = make_float4(y[1][4], y[1][5], y[1][6], y[1][7]);
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            float* r = srec + (size_t)(s * 256 + tid) * SREC;
+        for (int eq = 0; eq < LPG_E / 4; ++eq) {
+            float da[2][4], rd[2][4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) r[i] = y[s][i];
+            for (int k = 0; k < 4; ++k) {
+                const int e = eq * 4 + k;
+                float a0 = sp[LPG_Y * LPG_E + e], a1 = a0;
 #pragma unroll
-            for (int e = 0; e < LPG_E; ++e) {
-                float a = sp[LPG_Y * LPG_E + e];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) a = fmaf(y[s][i], sp[i * LPG_E + e], a);
-                r[8 + e] = a > 0.0f ? dp[s] * sp[LPG_Y * LPG_E + LPG_E + e] : 0.0f;     // da_e
-                r[8 + LPG_E + e] = fmaxf(a, 0.0f) * dp[s];                               // relu(a_e) * dp
+                for (int i = 0; i < 8; ++i) {
+                    const float wgt = sp[i * LPG_E + e];
+                    a0 = fmaf(y[0][i], wgt, a0);
+                    a1 = fmaf(y[1][i], wgt, a1);
+                }
+                const float w1 = sp[LPG_Y * LPG_E + LPG_E + e];
+                da[0][k] = a0 > 0.0f ? dp[0] * w1 : 0.0f;   rd[0][k] = fmaxf(a0, 0.0f) * dp[0];
+                da[1][k] = a1 > 0.0f ? dp[1] * w1 : 0.0f;   rd[1][k] = fmaxf(a1, 0.0f) * dp[1];
             }
-            r[8 + 2 * LPG_E] = dp[s];
+            reinterpret_cast<float4*>(r0 + 8)[eq] = make_float4(da[0][0], da[0][1], da[0][2], da[0][3]);
+            reinterpret_cast<float4*>(r0 + 8 + LPG_E)[eq] = make_float4(rd[0][0], rd[0][1], rd[0][2], rd[0][3]);
+            reinterpret_cast<float4*>(r1 + 8)[eq] = make_float4(da[1][0], da[1][1], da[1][2], da[1][3]);
+            reinterpret_cast<float4*>(r1 + 8 + LPG_E)[eq] = make_float4(rd[1][0], rd[1][1], rd[1][2], rd[1][3]);
         }
+        r0[8 + 2 * LPG_E] = dp[0];
+        r1[8 + 2 * LPG_E] = dp[1];
         __syncthreads();
-        if (tid < EM_TOTAL) {
-            // parameter tid: e_w0[i][e] -> y_i * da_e ; e_b0[e] -> da_e ; e_w1[e] -> relu(a_e) dp ; e_b1 -> dp
-            int ia = -1, ib;
-            if (tid < LPG_Y * LPG_E) { ia = tid / LPG_E; ib = 8 + tid % LPG_E; }
-            else if (tid < LPG_Y * LPG_E + LPG_E) ib = 8 + (tid - LPG_Y * LPG_E);
-            else if (tid < LPG_Y * LPG_E + 2 * LPG_E) ib = 8 + LPG_E + (tid - LPG_Y * LPG_E - LPG_E);
-            else ib = 8 + 2 * LPG_E;
-            float a_ = 0.0f;
-            for (int q = 0; q < 512; ++q) {
-                const float* r = srec + (size_t)q * SREC;
-                a_ = fmaf(ia >= 0 ? r[ia] : 1.0f, r[ib], a_);
+        if (nout == 4) {
+            const float* base = srec + (size_t)grp * 128 * EM_SREC;
+#pragma unroll 4
+            for (int q = 0; q < 128; ++q) {
+                const float* r = base + (size_t)q * EM_SREC;
+                const float4 v = *reinterpret_cast<const float4*>(r + src);
+                const float m = ysrc >= 0 ? r[ysrc] : 1.0f;
+                acc[0] = fmaf(m, v.x, acc[0]); acc[1] = fmaf(m, v.y, acc[1]);
+                acc[2] = fmaf(m, v.z, acc[2]); acc[3] = fmaf(m, v.w, acc[3]);
             }
-            acc += a_;
+        } else if (nout == 1) {
+            const float* base = srec + (size_t)grp * 128 * EM_SREC + src;
+            for (int q = 0; q < 128; ++q) acc[0] += base[(size_t)q * EM_SREC];
         }
         __syncthreads();
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < nout) part[grp][out0 + k] = acc[k];
+    __syncthreads();
     if (tid < EM_TOTAL) {
+        const float v = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
         float* o = partial + (size_t)blockIdx.x * EM_TOTAL + tid;
-        *o = accumulate ? *o + acc : acc;
+        *o = accumulate ? *o + v : v;
     }
 }
 
@@ -434,7 +465,7 @@ constexpr int WG_SPLITS = 37;        // token splits of the dWh GEMM (SIMT uses 
 constexpr int WG_SPLITS_SIMT = 32;
 constexpr int SM_SPLITS = 592;       // 4 per SM for the streaming kernels
 constexpr int EM_SPLITS = 296;
-constexpr int EM_SMEM = 2 * 256 * (LPG_Y + 2 * LPG_E + 1) * (int)sizeof(float);
+constexpr int EM_SMEM = 2 * 256 * EM_SREC * (int)sizeof(float);
 
 extern "C" int toued_lpg_wgrad_workspace_floats(void) {
     return WG_SPLITS * LPG_H * LPG_G + SM_SPLITS * SM_TOTAL + EM_SPLITS * EM_TOTAL;
