@@ -85,7 +85,10 @@ int toued_gru_forward(const float* x, const uint8_t* done, const float* lpg_para
 /* lpg_agent.py:60-85,119-120 + optim.py:6-11: closed-form actor/critic gradients, clip-by-global-
  * norm SGD, lifetime mask, step += keep, entropies of the updated nets.
  *   scalars f32[N][8] = {|g_actor|, |g_critic|, keep, critic_loss, pi_l2, y_l2, policy_entropy,
- *                        critic_entropy}                                                          */
+ *                        critic_entropy}
+ * toued_agent_update / toued_agent_backward take a temporary of 52 B x min(W*L, D) per agent for the launch from a
+ * library-owned, stream-ordered memory pool (cudaMallocFromPoolAsync / cudaFreeAsync on `stream`; the pool keeps
+ * its memory between calls), so concurrent calls on different streams do not share scratch.           */
 int toued_agent_update(const int32_t* obs, const uint8_t* action, const uint16_t* sorted_tok,
                        const float* pi_hat, const float* y_hat, const float* actor_in,
                        const float* critic_in, float* actor_out, float* critic_out,
