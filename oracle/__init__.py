@@ -20,7 +20,7 @@ third-party pieces it needs:
 What *is* pinned: the threefry2x32 block function against the three Random123 known-answer
 vectors (the same ones jax's own test-suite uses) and the ``split(PRNGKey(0))`` /
 ``uniform(PRNGKey(0))`` values printed in the public JAX documentation
-(tests/test_oracle_prng.py).  Everything downstream of those is "[3P-recall]".
+(tests/test_01_oracle_prng.py).  Everything downstream of those is "[3P-recall]".
 
 Layout
 ------

@@ -5,7 +5,7 @@ easy as 1, 2, 3", Random123) and the way jax==0.4.13 (setup/requirements-cpu.txt
 ``split`` / ``random_bits`` / ``uniform`` / ``bernoulli`` / ``choice`` / ``permutation`` from it
 (non-partitionable threefry, the 0.4.13 default).  [3P-recall]: jax is not installable here; the
 block function is pinned on the Random123 KATs and ``split`` / ``uniform`` on values printed in
-the public JAX docs (tests/test_oracle_prng.py).
+the public JAX docs (tests/test_01_oracle_prng.py).
 
 All functions are vectorised over leading "batch" axes of the key: a key is a ``uint32[..., 2]``
 array.  The CUDA kernels (to_ued_b200/csrc/prng.cuh) implement exactly the same derivation, so

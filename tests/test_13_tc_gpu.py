@@ -141,7 +141,7 @@ def test_meta_gradient_tensor_core_path(built_lib, mode, cond, n, w, monkeypatch
     from oracle import prng
     from oracle.agents import AgentTables
     from oracle.meta import lpg_meta_grad_train_step as o_step
-    from test_meta_grad_gpu import _run
+    from test_14_meta_grad_gpu import _run
     K = 5           # n = 3: ragged last tile through the whole tensor-core chain (forward, BPTT, weight gradients);
                     # w = 8: 24 sequences = one partial tile, not a multiple of 32 (streaming head-gradient kernel)
     c = Case(mode, n=n, w=w, seed=7, cond=cond, table_scale=0.3, lifetimes=[250, 3, 250, 250][:n], steps=[0, 0, 17, 246][:n])

@@ -13,7 +13,7 @@
 //     d L / d pi_hat_k[tok] = <w, grad_theta log(pi+1e-8)[tok]> / T        (-> LPG backward)
 //     lam_k = lam_{k+1} + grad_theta <w, g_k(theta)>                        (Hessian-vector product)
 // and likewise for the critic with the KL(y_t || y_hat) loss.  All closed form for softmax tables;
-// the formulas were checked against torch.autograd to 1e-15 in fp64 (tests/test_meta_grad_gpu.py
+// the formulas were checked against torch.autograd to 1e-15 in fp64 (tests/test_14_meta_grad_gpu.py
 // checks this kernel against the autograd oracle).
 //
 // Every row scatter is a segmented sum over the row-sorted token list: deterministic, no atomics.

@@ -17,17 +17,37 @@ def _nvcc():
     return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 
-def build(verbose=False, force=False):
+# diagnostic variants: name -> extra -D flags; built into libtoued_<name>.so next to the production library
+VARIANTS = {
+    # delays the odd-pass epilogue warps of gru_forward_tc at pass 13 so that an x-tile write-after-read hazard
+    # (if present) fires on every step (tests/diag_nondeterminism.py)
+    "probe": ["-DTOUED_RACE_PROBE=1"],
+    # random delays in front of every mbarrier wait: schedule fuzzing of the warp-specialised kernels
+    "fuzz": ["-DTOUED_FUZZ=1"],
+    "fuzz_old": ["-DTOUED_FUZZ=1", "-DTOUED_XTILE_OLD=1"],
+    "old": ["-DTOUED_XTILE_OLD=1"],
+    "probe_old": ["-DTOUED_RACE_PROBE=1", "-DTOUED_XTILE_OLD=1"],      # the round-1 x-tile writer (set 0)
+}
+
+
+def build(verbose=False, force=False, variant=""):
+    global OUT
+    if variant:
+        return _build(verbose, force, os.path.join(HERE, "..", f"libtoued_{variant}.so"),
+                      os.path.join(HERE, f"build_{variant}"), VARIANTS[variant])
+    return _build(verbose, force, OUT, os.path.join(HERE, "build"), [])
+
+
+def _build(verbose, force, OUT, objdir, extra):
     srcs = sorted(f for f in os.listdir(HERE) if f.endswith(".cu"))
     hdrs = sorted(f for f in os.listdir(HERE) if f.endswith(".cuh")) + ["../../include/toued.h"]
     hsig = hashlib.sha1(b"".join(open(os.path.join(HERE, h), "rb").read() for h in hdrs)).hexdigest()
-    objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs, rebuilt = [], False
     for s in srcs:
         src = os.path.join(HERE, s)
         obj = os.path.join(objdir, s[:-3] + ".o")
-        flags = FLAGS.get(s, COMMON)
+        flags = list(FLAGS.get(s, COMMON)) + list(extra)
         sig = hashlib.sha1(open(src, "rb").read() + hsig.encode() + " ".join(flags).encode()).hexdigest()
         sigf = obj + ".sig"
         if force or not os.path.exists(obj) or not os.path.exists(sigf) or open(sigf).read() != sig:
@@ -48,4 +68,5 @@ def build(verbose=False, force=False):
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, variant=var[0] if var else ""))

@@ -201,7 +201,20 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+#if defined(TOUED_FUZZ)
+// diagnostic build (csrc/build.py::VARIANTS["fuzz"]): one in eight barrier waits first sleeps for a pseudo-random
+// time of up to 16 us, which shuffles the relative progress of the warp roles of every mbarrier-synchronised kernel.
+// A correctly synchronised kernel gives bit-identical results under any such schedule.
+__device__ __forceinline__ void fuzz_delay() {
+    unsigned c = (unsigned)clock() ^ ((threadIdx.x >> 5) * 2654435761u) ^ (blockIdx.x * 40503u);
+    c ^= c >> 13; c *= 0x5bd1e995u; c ^= c >> 15;
+    if ((c & 7u) == 0) __nanosleep((c >> 8) & 0x3FFFu);
+}
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if defined(TOUED_FUZZ)
+    fuzz_delay();
+#endif
     asm volatile(
         "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"

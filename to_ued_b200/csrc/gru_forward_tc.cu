@@ -266,8 +266,17 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
 #pragma unroll
         for (int c = 0; c < LPG_Y; ++c) b_heads[1 + c] = lpg[o.b_y + c];
         for (int t = L - 1, step = 0; t >= 0; --t, ++step) {
-            // x_{t-1} (the next processed step) goes into the other x tile as fp16 (one thread per row)
+            // x_{t-1} (the next processed step) goes into the other x tile as fp16 (one thread per row).  That tile was
+            // the A operand of the input-projection MMAs of the PREVIOUS step, the last of which (pass 15) belongs to
+            // set 1: only a set-1 warp has observed acc_full of that pass, i.e. knows that every MMA reading the tile
+            // has completed.  (Round 1 wrote it from set 0, whose last pass is 14: when set 1 lagged by one pass the
+            // MMA of pass 15 read x of the wrong time step for 16 units -- the source of the run-to-run differences
+            // of the BASELINE-size step; tests/diag_nondeterminism.py reproduces it with the probe build.)
+#if defined(TOUED_XTILE_OLD)
             if (set == 0 && hf == 0 && t > 0) {
+#else
+            if (set == 1 && hf == 0 && t > 0) {
+#endif
                 uint4 pk = make_uint4(0u, 0u, 0u, 0u);
                 if (rv) {
                     const float4* xp = reinterpret_cast<const float4*>(x + ((size_t)(t - 1) * R + row) * LPG_XP);
@@ -286,6 +295,9 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
             for (int p = set; p < FT_NPASS; p += 2) {
                 const uint32_t it = (uint32_t)step * FT_NPASS + p;
                 const int a = set;
+#if defined(TOUED_RACE_PROBE)
+                if (set == 1 && p == 13) __nanosleep(20000);      // diagnostic build: let set 0 run a full pass ahead
+#endif
                 mbar_wait(&acc_full[a], (it >> 1) & 1);
                 tc_fence_after();
                 float ar[8], az[8], an[8], ai[8];
@@ -369,7 +381,9 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                     }
                 }
             }
-            // this warp's part of h_t is in tensor memory: signal the MMA warp (no shared-memory traffic, no proxy fence)
+            // this warp's part of h_t is in tensor memory: signal the MMA warp.  The x tile of the next step was written
+            // with generic-proxy stores and is read by the tensor core (async proxy): proxy fence before the arrival.
+            fence_proxy_async_smem();
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
