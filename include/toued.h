@@ -186,6 +186,19 @@ int toued_es_tell(const float* candidates, const float* fitness, float* mean, fl
                   int popsize, int n_params, int cand_stride, float sigma, float lrate, float beta1,
                   float beta2, float eps, int gen_counter, float mean_decay, void* stream);
 
+/* Multi-GPU ES (agents sharded over ranks, antithetic pairs kept on one rank; SURVEY.md section 8e, reference
+ * meta/train.py:203-216): ask_shard writes the candidates of the pairs [pair_offset, pair_offset + n_pairs) of a global
+ * population exactly as toued_es_ask would (candidates f32[2 * n_pairs][cand_stride]); grad_partial writes this rank's
+ * sum_i noise_i * (-fitness_i) into grad_sum f32[n_params] (the caller all-reduces it over the ranks); es_adam is the
+ * second half of toued_es_tell on the reduced sum.                                                        */
+int toued_es_ask_shard(const uint32_t* key, const float* mean, float sigma, float* candidates, int popsize_global,
+                       int n_params, int cand_stride, int pair_offset, int n_pairs, void* stream);
+int toued_es_grad_partial(const float* candidates, const float* fitness, const float* mean, float* grad_sum,
+                          int n_members, int n_params, int cand_stride, float sigma, void* stream);
+int toued_es_adam(const float* grad_sum, float* mean, float* m, float* v, int popsize_global, int n_params,
+                  float sigma, float lrate, float beta1, float beta2, float eps, int gen_counter, float mean_decay,
+                  void* stream);
+
 /* ---- double-oracle Nash solver (environments/nash_sampler.py:24-58, util/projection.py:9-38) ------ */
 /* game f32[n][n] (row player x minimises x^T G y), supports = first x_nz / y_nz coordinates, n <= 1024.
  * Averaged iterates of num_iters projected-gradient steps (reference: 10,000 steps, lr 0.01).        */

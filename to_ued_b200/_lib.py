@@ -62,6 +62,9 @@ SIGNATURES = {
     "toued_projection_simplex": [_P, _I, _I, _P],
     "toued_es_ask": [_P, _P, _F, _P, _I, _I, _I, _P],
     "toued_es_tell": [_P] * 5 + [_I, _I, _I] + [_F] * 5 + [_I, _F, _P],
+    "toued_es_ask_shard": [_P, _P, _F, _P, _I, _I, _I, _I, _I, _P],
+    "toued_es_grad_partial": [_P] * 4 + [_I, _I, _I, _F, _P],
+    "toued_es_adam": [_P] * 4 + [_I, _I] + [_F] * 5 + [_I, _F, _P],
     "toued_a2c_update": [_P] * 12 + [_I] * 4 + [_F] * 6 + [_I, _P],
     "toued_a2c_train": [_P] * 15 + [_I] * 7 + [_F] * 6 + [_I, _P],
     "toued_init_tables": [_P] * 3 + [_I] * 3 + [_P],

@@ -12,6 +12,13 @@ The reference re-creates *every* agent on every call of ``sample`` and then mask
 the same result.  ``actor_state.step`` is mirrored on the host (it evolves deterministically:
 ``step <- step + 1`` while ``step < lifetime``), so ``sample`` never synchronises with the device.
 
+Multi-GPU: rank r holds agents [r n, (r + 1) n) of the global batch.  ``sample`` and
+``initial_sample`` derive every key for the GLOBAL batch (``split(rng, n_global)``) and keep the local slice, the
+level buffer is replicated and updated identically on every rank from all-gathered ``(buffer_id, score,
+terminated)`` triples, so the levels, ids and init keys of agent i do not depend on the number of ranks.  The
+host-side decisions are separated from the device work (``_plan_sample`` / ``_recreate``) so that the
+rank-independence is testable without a GPU (tests/test_05_multi_rank_cpu.py).
+
 Reproduced quirks: Q3 (``new=level_buffer.active.at[reset_ids].set(True)``), Q10 (buffer ids of random
 levels are 0)."""
 from __future__ import annotations
@@ -24,6 +31,7 @@ import torch
 
 from .. import _lib
 from ..util import prng
+from ..util import dist as udist
 from ..util.data import AgentState, Level, TrainState
 from ..agents.agents import AgentHyperparams, eval_agent
 from ..models.agent import init_tables
@@ -72,6 +80,7 @@ class LevelSampler:
 
     def __init__(self, args, device="cuda"):
         self.device = device
+        self.rank, self.world = udist.rank_world()
         self.env_name, self.env_mode, self.env_workers = args.env_name, args.env_mode, args.env_workers
         self.env_kwargs, self.max_rollout_len, self.max_lifetime = get_env_spec(self.env_name, self.env_mode)
         self.env = get_env(self.env_name, self.env_kwargs)
@@ -99,10 +108,12 @@ class LevelSampler:
         """level_sampler.py:98-101 (vmapped over keys)."""
         return reset_env_params(rng, self.env_name, self.env_mode)
 
-    def _sample_random_levels(self, rng, batch_size: int) -> Level:
-        """level_sampler.py:268-271 (Q10: buffer ids are zeros)."""
-        params, lifetimes = self._sample_env_params(prng.split(np.asarray(rng, np.uint32), batch_size))
-        return Level(params, lifetimes, np.zeros(batch_size, np.int32))
+    def _sample_random_levels(self, rng, batch_size: int, sl: slice = slice(None)) -> Level:
+        """level_sampler.py:268-271 (Q10: buffer ids are zeros).  ``sl``: the part of the batch to generate (one key
+        per level, so a slice of the keys gives exactly that slice of the levels)."""
+        keys = prng.split(np.asarray(rng, np.uint32), batch_size)[sl]
+        params, lifetimes = self._sample_env_params(keys)
+        return Level(params, lifetimes, np.zeros(len(keys), np.int32))
 
     # ------------------------------------------------------------------------------ agents
     def _device_level(self, level: Level) -> Level:
@@ -123,60 +134,80 @@ class LevelSampler:
         return AgentState(actor, critic, level, env_obs, env_state, np.zeros(len(level), np.int32))
 
     def initial_sample(self, rng, level_buffer: Optional[LevelBuffer], batch_size: int, create_value_critics: bool):
-        """level_sampler.py:103-132"""
+        """level_sampler.py:103-132.  ``batch_size`` is the GLOBAL number of agents; with several ranks the agents
+        [rank * n, (rank + 1) * n) are created here (same levels and keys as in a single-rank run)."""
         rng = np.asarray(rng, np.uint32)
+        sl = udist.local_slice(batch_size)
         if self.score_function == "random":
             rng, _rng = prng.split(rng, 2)
-            levels = self._sample_random_levels(_rng, batch_size)
+            levels = self._sample_random_levels(_rng, batch_size, sl)
         else:
-            levels = _index_level(level_buffer.level, np.arange(batch_size))
+            levels = _index_level(level_buffer.level, np.arange(batch_size)[sl])
             level_buffer = level_buffer.replace(active=np.arange(self.buffer_size) < batch_size)
         rng, _rng = prng.split(rng, 2)
-        agent_states = self._create_agent(prng.split(_rng, batch_size), levels)
+        agent_states = self._create_agent(prng.split(_rng, batch_size)[sl], levels)
         value_critics = None
         if create_value_critics:
             from ..agents.agents import create_value_critic
             rng, _rng = prng.split(rng, 2)
-            value_critics = create_value_critic(prng.split(_rng, batch_size), self.agent_hypers, self.obs_shape, self.device)
+            value_critics = create_value_critic(prng.split(_rng, batch_size)[sl], self.agent_hypers, self.obs_shape, self.device)
         return level_buffer, agent_states, value_critics
 
     # ------------------------------------------------------------------------------ sample
     def sample(self, rng, level_buffer: Optional[LevelBuffer], old_agents: AgentState, old_value_critics):
         """Update level buffer and sample new levels for terminated agents (level_sampler.py:134-266)."""
+        score_fn = lambda keys, only: self._compute_algorithmic_regret(keys, old_agents, only=only)
+        level_buffer, plan = self._plan_sample(rng, level_buffer, old_agents.host_step, old_agents.level,
+                                               old_value_critics is not None, score_fn)
+        if plan is None:
+            return level_buffer, old_agents, old_value_critics
+        terminated, new_levels, agent_keys, value_keys = plan
+        return (level_buffer,) + self._recreate(terminated, new_levels, agent_keys, value_keys, old_agents, old_value_critics)
+
+    def _plan_sample(self, rng, level_buffer, host_step, old_level: Level, have_value_critics: bool, score_fn):
+        """Host-side decisions of ``sample`` for this rank's agents: (new level buffer, plan) with plan = None when no
+        agent of the GLOBAL batch terminated, else (terminated[n_local], new levels[n_local], agent init keys
+        [n_local, 2], value-critic init keys or None).  Every draw is made for the global batch and sliced, and the
+        buffer is updated from all-gathered triples: the result does not depend on the number of ranks.
+        ``score_fn(keys[n_local, 2], only=mask) -> f32[n_local]`` is the regret evaluation (device work)."""
         rng = np.asarray(rng, np.uint32)
-        step = old_agents.host_step
-        terminated = step >= old_agents.level.lifetime
-        batch_size = terminated.shape[0]
+        terminated = np.asarray(host_step) >= old_level.lifetime
+        n_local = terminated.shape[0]
+        batch_size = n_local * self.world                      # global
+        sl = slice(self.rank * n_local, (self.rank + 1) * n_local)
+        terminated_g = udist.all_gather_host(terminated)
 
         if self.score_function == "random":
             rng, _rng = prng.split(rng, 2)
             if terminated.any():
-                new_levels = _where_level(terminated, self._sample_random_levels(_rng, batch_size), old_agents.level)
+                new_levels = _where_level(terminated, self._sample_random_levels(_rng, batch_size, sl), old_level)
             else:
-                new_levels = old_agents.level
+                new_levels = old_level
         elif self.score_function == "frozen":
             rng, _rng = prng.split(rng, 2)
             p_uniform = np.ones(self.buffer_size, np.float32) / np.float32(self.buffer_size)
-            level_ids = _choice_p_many(_rng, p_uniform, batch_size)
-            new_levels = _where_level(terminated, _index_level(level_buffer.level, level_ids), old_agents.level)
+            level_ids = _choice_p_many(_rng, p_uniform, batch_size)[sl]
+            new_levels = _where_level(terminated, _index_level(level_buffer.level, level_ids), old_level)
         else:
             rng, _rng = prng.split(rng, 2)
             level_buffer = self._reset_lowest_scoring(_rng, level_buffer, batch_size)
             if self.score_function != "alg_regret":
                 raise NotImplementedError(f"Level score function {self.score_function} is not implemented.")
             rng, _rng = prng.split(rng, 2)
-            score = self._compute_algorithmic_regret(prng.split(_rng, batch_size), old_agents, only=terminated)
-            old_ids = old_agents.level.buffer_id
+            score = np.asarray(score_fn(prng.split(_rng, batch_size)[sl], terminated), np.float32)
+            # every rank applies the same update: all-gather of (buffer_id, score, terminated) per agent
+            old_ids = udist.all_gather_host(old_level.buffer_id.astype(np.int32))
+            score = udist.all_gather_host(score)
             # sequential scatter == .at[old_ids].set(...) with duplicate ids resolved last-wins
             sc, ac, nw = level_buffer.score.copy(), level_buffer.active.copy(), level_buffer.new.copy()
-            t_score = np.where(terminated, score, level_buffer.score[old_ids])
-            t_active = np.where(terminated, False, level_buffer.active[old_ids])
-            t_new = np.where(terminated, False, level_buffer.new[old_ids])
+            t_score = np.where(terminated_g, score, level_buffer.score[old_ids])
+            t_active = np.where(terminated_g, False, level_buffer.active[old_ids])
+            t_new = np.where(terminated_g, False, level_buffer.new[old_ids])
             sc[old_ids], ac[old_ids], nw[old_ids] = t_score, t_active, t_new
             level_buffer = level_buffer.replace(score=sc, active=ac, new=nw)
             rng, replay_rng, random_rng = prng.split(rng, 3)
-            replay_levels = self._replay_from_buffer(replay_rng, level_buffer, batch_size)
-            random_levels = self._sample_random_from_buffer(random_rng, level_buffer, batch_size)
+            replay_ids = self._replay_ids(replay_rng, level_buffer, batch_size)
+            random_ids = self._random_ids(random_rng, level_buffer, batch_size)
             rng, _rng = prng.split(rng, 2)
             n_to_replay = int((prng.uniform(_rng, (batch_size,)) < np.float32(self.p_replay)).sum())
             use_replay = np.arange(batch_size) < n_to_replay
@@ -184,22 +215,22 @@ class LevelSampler:
             use_replay = use_replay & (n_replayable >= batch_size)
             rng, _rng = prng.split(rng, 2)
             use_replay = use_replay[prng.shuffle_prefix(_rng, batch_size, batch_size)]      # random.permutation
-            new_levels = _where_level(use_replay, replay_levels, random_levels)
-            new_levels = _where_level(terminated, new_levels, old_agents.level)
+            new_ids = np.where(terminated_g, np.where(use_replay, replay_ids, random_ids), old_ids).astype(np.int32)
+            new_levels = _where_level(terminated, _index_level(level_buffer.level, new_ids[sl]), old_level)
             ac = level_buffer.active.copy()
-            ac[new_levels.buffer_id] = True
+            ac[new_ids] = True
             level_buffer = level_buffer.replace(active=ac)
 
         # --- Initialise new agents and environment workers for terminated agents ---
         rng, _rng = prng.split(rng, 2)
-        agent_keys = prng.split(_rng, batch_size)
+        agent_keys = prng.split(_rng, batch_size)[sl]
         value_keys = None
-        if old_value_critics is not None:
+        if have_value_critics:
             rng, _rng = prng.split(rng, 2)
-            value_keys = prng.split(_rng, batch_size)
-        if not terminated.any():
-            return level_buffer, old_agents, old_value_critics
-        return (level_buffer,) + self._recreate(terminated, new_levels, agent_keys, value_keys, old_agents, old_value_critics)
+            value_keys = prng.split(_rng, batch_size)[sl]
+        if not terminated_g.any():
+            return level_buffer, None
+        return level_buffer, (terminated, new_levels, agent_keys, value_keys)
 
     def _recreate(self, terminated, new_levels: Level, agent_keys, value_keys, old_agents: AgentState, old_vc):
         """Masked version of level_sampler.py:236-265: only terminated agents get new tables / envs."""
@@ -266,27 +297,30 @@ class LevelSampler:
                                     active=_set_rows(level_buffer.active, reset_ids, False),
                                     new=_set_rows(level_buffer.active, reset_ids, True))
 
-    def _replay_from_buffer(self, rng, level_buffer: LevelBuffer, batch_size: int) -> Level:
-        """level_sampler.py:355-387"""
+    def _replay_ids(self, rng, level_buffer: LevelBuffer, batch_size: int) -> np.ndarray:
+        """level_sampler.py:355-387 (ids of the replayed levels)."""
         invalid = level_buffer.new | level_buffer.active
         scores = np.exp(level_buffer.score / np.float32(self.score_temperature)).astype(np.float32)
         scores = np.where(invalid, np.float32(0.0), scores)
         scores = (scores / scores.sum(dtype=np.float32)).astype(np.float32)
         p_replay = np.where(self.buffer_size - invalid.sum() < batch_size, np.ones_like(scores), scores)
         if self.score_transform == "rank":
-            level_ids = np.argsort(p_replay, kind="stable")[::-1][:batch_size]
-        elif self.score_transform == "proportional":
+            return np.argsort(p_replay, kind="stable")[::-1][:batch_size].astype(np.int32)
+        if self.score_transform == "proportional":
             _rng = prng.split(np.asarray(rng, np.uint32), 2)[1]
-            level_ids = _gumbel_topk(_rng, p_replay, batch_size)
-        else:
-            raise NotImplementedError(f"Level score transform {self.score_transform} is not implemented.")
-        return _index_level(level_buffer.level, level_ids)
+            return _gumbel_topk(_rng, p_replay, batch_size)
+        raise NotImplementedError(f"Level score transform {self.score_transform} is not implemented.")
 
-    def _sample_random_from_buffer(self, rng, level_buffer: LevelBuffer, batch_size: int) -> Level:
+    def _replay_from_buffer(self, rng, level_buffer: LevelBuffer, batch_size: int) -> Level:
+        return _index_level(level_buffer.level, self._replay_ids(rng, level_buffer, batch_size))
+
+    def _random_ids(self, rng, level_buffer: LevelBuffer, batch_size: int) -> np.ndarray:
         """level_sampler.py:389-408: new (unevaluated), inactive levels, without replacement."""
         mask = level_buffer.new & ~level_buffer.active
-        level_ids = prng.masked_topk(np.asarray(rng, np.uint32), mask, batch_size)
-        return _index_level(level_buffer.level, level_ids)
+        return prng.masked_topk(np.asarray(rng, np.uint32), mask, batch_size)
+
+    def _sample_random_from_buffer(self, rng, level_buffer: LevelBuffer, batch_size: int) -> Level:
+        return _index_level(level_buffer.level, self._random_ids(rng, level_buffer, batch_size))
 
     @property
     def num_actions(self):

@@ -6,6 +6,11 @@ Antithetic task sampling: candidate 2i and 2i+1 are mean +/- sigma z_i and both 
 the same level; fitness is the rank within the pair.  Every candidate has its own LPG parameter vector, so
 the LPG forward runs with a per-agent parameter stride (one CTA per agent in the exact-fp32 GRU kernel).
 
+Multi-GPU: rank r trains the pairs of its own agents (``toued_es_ask_shard`` draws exactly
+the global population's candidates for them), the pairwise rank fitness is local to a pair, the gradient estimate
+``noise^T fitness`` is summed over ranks with one all-reduce, the raw fitness is all-gathered for the metrics, and every
+rank applies the identical Adam step to its replica of the ES mean.
+
 Reproduced: Q11 (fitness from ``env_workers`` eval workers), Q12 (``train_state.params`` is never refreshed;
 the ES mean — which evosax initialises to zeros — is the result; exposed as ``ESTrainState.mean``)."""
 from __future__ import annotations
@@ -17,6 +22,7 @@ import torch
 
 from .. import _lib
 from ..util import prng
+from ..util import dist as udist
 from ..util.data import AgentState, LpgHyperparams, Level
 from ..agents.lpg_agent import train_lpg_agent
 from ..agents.agents import eval_agent
@@ -95,10 +101,13 @@ def lpg_es_train_step(rng, lpg_train_state: ESTrainState, agent_states: AgentSta
     Returns (lpg_train_state, agent_states, None, metrics)."""
     env = rollout_manager.env
     strat, st = lpg_train_state.strategy, lpg_train_state.es_state
-    N, W = agent_states.env_state.packed.shape
-    popsize, P = strat.popsize, strat.num_dims
-    if popsize != 2 * N:
-        raise ValueError(f"ES population ({popsize}) must be twice the number of agents ({N})")
+    N, W = agent_states.env_state.packed.shape                  # local agents
+    rank_, world = udist.rank_world()
+    pop_global, P = strat.popsize, strat.num_dims
+    popsize = 2 * N                                             # local members
+    if pop_global != popsize * world:
+        raise ValueError(f"ES population ({pop_global}) must be twice the number of agents ({N} x {world} ranks)")
+    pair_off = rank_ * N
     dev = agent_states.actor_state.params.device
     p, s = _lib.ptr, _lib.stream_ptr()
     rng = np.asarray(rng, np.uint32)
@@ -107,12 +116,16 @@ def lpg_es_train_step(rng, lpg_train_state: ESTrainState, agent_states: AgentSta
     cand = torch.zeros((popsize, Pp), dtype=torch.float32, device=dev)
     if candidates is None:
         kd = torch.from_numpy(np.ascontiguousarray(k_ask).view(np.int32)).to(dev)
-        _lib.call("toued_es_ask", p(kd), p(st["mean"]), float(st["sigma"]), p(cand), popsize, P, Pp, s)
+        if world == 1:
+            _lib.call("toued_es_ask", p(kd), p(st["mean"]), float(st["sigma"]), p(cand), popsize, P, Pp, s)
+        else:
+            _lib.call("toued_es_ask_shard", p(kd), p(st["mean"]), float(st["sigma"]), p(cand), pop_global, P, Pp,
+                      pair_off, N, s)
     else:
         cand[:, :P] = candidates
     rep = _repeat2(agent_states, W, env.max_n_objs)
     rng, k = prng.split(rng, 2)
-    keys = prng.split(k, popsize)
+    keys = prng.split(k, pop_global)[2 * pair_off:2 * pair_off + popsize]
     ks = prng.split(keys, 2)
     k_eval, k_train = ks[:, 0, :], ks[:, 1, :]                  # rng, _rng = split(rng) (meta/train.py:172)
 
@@ -164,16 +177,28 @@ def lpg_es_train_step(rng, lpg_train_state: ESTrainState, agent_states: AgentSta
         env_obs=new_obs[pick], env_state=EnvState(new_state[pick], env.max_n_objs), host_step=host_step)
     # --- tell ---
     mean = st["mean"].clone(); m = st["m"].clone(); v = st["v"].clone()
-    _lib.call("toued_es_tell", p(cand), p(rank), p(mean), p(m), p(v), popsize, P, Pp, float(st["sigma"]), float(st["lrate"]),
-              float(strat.beta_1), float(strat.beta_2), float(strat.eps), int(st["gen_counter"]), float(strat.mean_decay), s)
+    if world == 1:
+        _lib.call("toued_es_tell", p(cand), p(rank), p(mean), p(m), p(v), popsize, P, Pp, float(st["sigma"]), float(st["lrate"]),
+                  float(strat.beta_1), float(strat.beta_2), float(strat.eps), int(st["gen_counter"]), float(strat.mean_decay), s)
+        fitness_all = fitness
+    else:
+        # this rank's part of noise^T fitness -> all-reduce -> identical Adam step on every rank (meta/train.py:203-216)
+        gsum = torch.empty(P, dtype=torch.float32, device=dev)
+        _lib.call("toued_es_grad_partial", p(cand), p(rank), p(mean), p(gsum), popsize, P, Pp, float(st["sigma"]), s)
+        udist.all_reduce_sum(gsum)
+        _lib.call("toued_es_adam", p(gsum), p(mean), p(m), p(v), pop_global, P, float(st["sigma"]), float(st["lrate"]),
+                  float(strat.beta_1), float(strat.beta_2), float(strat.eps), int(st["gen_counter"]), float(strat.mean_decay), s)
+        fitness_all = udist.all_gather_device(fitness)           # 2 N_global floats, for the metrics
+        udist.all_reduce_sum(msum)
     new_es = {"mean": mean, "m": m, "v": v,
               "sigma": max(st["sigma"] * strat.sigma_decay, strat.sigma_limit),
               "lrate": max(st["lrate"] * strat.lrate_decay, strat.lrate_limit),
               "gen_counter": st["gen_counter"] + 1}
     metrics = {
-        "fitness": {"mean": fitness.mean(), "min": fitness.min(), "max": fitness.max(), "var": fitness.var(unbiased=False)},
-        "lpg_agent": {k_: msum[i] / popsize for i, k_ in enumerate(("policy_l2", "policy_entropy", "critic_loss",
+        "fitness": {"mean": fitness_all.mean(), "min": fitness_all.min(), "max": fitness_all.max(),
+                    "var": fitness_all.var(unbiased=False)},
+        "lpg_agent": {k_: msum[i] / pop_global for i, k_ in enumerate(("policy_l2", "policy_entropy", "critic_loss",
                                                                     "critic_l2", "critic_entropy"))},
-        "_fitness": fitness, "_candidates": cand[:, :P],
+        "_fitness": fitness_all, "_candidates": cand[:, :P],
     }
     return lpg_train_state.replace(es_state=new_es), agents_out, None, metrics

@@ -35,13 +35,13 @@ def make_train(args, rank=0, world=1):
         train_state = create_lpg_train_state(lpg_rng, args)
         level_sampler = LevelSampler(args)
         level_buffer = level_sampler.initialize_buffer(buffer_rng)
-        # --- Initialize agents and value critics --- (every rank derives the global key set and keeps its slice)
+        # --- Initialize agents and value critics --- (the sampler derives the keys of the global batch and creates
+        #     this rank's slice; the level buffer is replicated and stays identical on every rank)
         require_value_critic = not args.use_es
         rng, _rng = prng.split(rng, 2)
         level_buffer, agent_states, value_critic_states = level_sampler.initial_sample(
             _rng, level_buffer, args.num_agents, require_value_critic)
-        if world > 1:
-            agent_states, value_critic_states = _shard(agent_states, value_critic_states, rank, n_local)
+        assert len(agent_states.level) == n_local
         lpg_train_step_fn = make_lpg_train_step(args, level_sampler)
         history = []
         for _ in range(args.train_steps):          # Q1: the reference runs a fixed 10 steps
@@ -59,6 +59,8 @@ def make_train(args, rank=0, world=1):
 
 
 def _shard(agents, vcs, rank, n_local):
+    """Rank ``rank``'s slice [rank * n_local, (rank + 1) * n_local) of a batch of agents (utility for callers that
+    build the global batch themselves; ``LevelSampler.initial_sample`` creates the local slice directly)."""
     from to_ued_b200.util.data import Level
     from to_ued_b200.environments.gridworld.gridworld import EnvState
     sl = slice(rank * n_local, (rank + 1) * n_local)
