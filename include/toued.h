@@ -86,15 +86,16 @@ int toued_gru_forward(const float* x, const uint8_t* done, const float* lpg_para
  * norm SGD, lifetime mask, step += keep, entropies of the updated nets.
  *   scalars f32[N][8] = {|g_actor|, |g_critic|, keep, critic_loss, pi_l2, y_l2, policy_entropy,
  *                        critic_entropy}
- * toued_agent_update / toued_agent_backward take a temporary of 52 B x min(W*L, D) per agent for the launch from a
- * library-owned, stream-ordered memory pool (cudaMallocFromPoolAsync / cudaFreeAsync on `stream`; the pool keeps
- * its memory between calls), so concurrent calls on different streams do not share scratch.           */
+ * toued_agent_update / toued_agent_backward need a temporary of 52 B x min(W*L, D) per agent for the duration of the
+ * launch: run_scratch, f32[toued_agent_scratch_floats(N, W, L, D)], provided by the caller like every other buffer
+ * (calls that may run concurrently on different streams need distinct scratch buffers).               */
+int toued_agent_scratch_floats(int n_agents, int n_workers, int rollout_len, int obs_dim);
 int toued_agent_update(const int32_t* obs, const uint8_t* action, const uint16_t* sorted_tok,
                        const float* pi_hat, const float* y_hat, const float* actor_in,
                        const float* critic_in, float* actor_out, float* critic_out,
                        const void* levels, int32_t* step, float* scalars, int n_agents,
                        int n_workers, int rollout_len, int obs_dim, float lr_actor, float lr_critic,
-                       float max_grad_norm, float agent_target_coeff, void* stream);
+                       float max_grad_norm, float agent_target_coeff, float* run_scratch, void* stream);
 
 /* ---- meta-gradient (meta/train.py:14-130): what the reference gets from jax.grad ---------------- */
 
@@ -120,7 +121,7 @@ int toued_agent_backward(const int32_t* obs, const uint8_t* action, const uint16
                          float lr_actor, float lr_critic, float max_grad_norm,
                          float agent_target_coeff, float policy_entropy_coeff,
                          float target_entropy_coeff, float policy_l2_coeff, float target_l2_coeff,
-                         float grad_scale, void* stream);
+                         float grad_scale, float* run_scratch, void* stream);
 
 /* whT f32[768][256] = transpose of the recurrent matrix Wh (once per meta-step).                 */
 int toued_transpose_wh(const float* lpg_params, float* whT, void* stream);
@@ -146,13 +147,20 @@ int toued_lpg_wgrad_workspace_offset(int which);   /* float offset of the {0: Wh
 int toued_lpg_wgrad_embed(const int32_t* obs, const uint8_t* done, const float* critic, const float* lpg_params,
                           const float* dx, float* workspace, int n_agents, int n_workers, int rollout_len,
                           int obs_dim, int lifetime_conditioning, int accumulate, void* stream);
-/* wh_splits: number of Wh partial slices to sum (32 after toued_lpg_wgrad, toued_wgrad_tc_splits() after
- * toued_lpg_wgrad_tc).                                                                              */
-int toued_reduce_partials(const float* workspace, float* grad, int lifetime_conditioning, int wh_splits, void* stream);
+/* wh_splits / sm_splits: how many dWh and small-parameter partial areas the producer filled --
+ * toued_lpg_wgrad_splits(0) / (1) after toued_lpg_wgrad, toued_wgrad_tc_splits() / toued_wgrad_tc_small_splits() after
+ * toued_lpg_wgrad_tc.  Areas beyond these counts are never read.                                         */
+int toued_lpg_wgrad_splits(int which);
+int toued_reduce_partials(const float* workspace, float* grad, int lifetime_conditioning, int wh_splits,
+                          int sm_splits, void* stream);
 
 /* models/optim.py:12-17: optax.scale_by_adam -> scale(lr) -> scale(-1); count is 1-based.          */
 int toued_adam(float* params, const float* grad, float* mu, float* nu, int n, int count, float lr,
                float b1, float b2, float eps, void* stream);
+/* the same step with the number of updates done so far in device memory (count_dev i32[1], incremented by the call):
+ * no host-side state, so the call can be part of a captured CUDA graph (meta/graph.py).               */
+int toued_adam_dev(float* params, const float* grad, float* mu, float* nu, int* count_dev, int n, float lr,
+                   float b1, float b2, float eps, void* stream);
 
 /* ---- A2C antagonist (agents/a2c.py:19-76), used by the algorithmic-regret level score ---------- */
 /* critic_in/out: value tables f32[N][D][8] (column 0).  scalars f32[N][4] = {actor_loss, critic_loss,
@@ -279,6 +287,7 @@ int toued_gru_backward_tc(const uint8_t* done, const float* lpg_params, const vo
 /* Tensor-core weight gradients from the token tile images (hpimg from the forward, dgimg from the
  * backward) + streaming small gradients; partial areas of the toued_lpg_wgrad workspace.             */
 int toued_wgrad_tc_splits(void);
+int toued_wgrad_tc_small_splits(void);
 int toued_lpg_wgrad_tc(const void* hpimg, const void* dgimg, const void* ximg, const void* h16,
                        const float* d_pi_hat, const float* dl, float* wh_partials, float* small_partials,
                        int n_agents, int n_workers, int rollout_len, int accumulate, void* stream);

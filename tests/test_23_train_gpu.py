@@ -30,6 +30,24 @@ def test_train_loop_runs_recreates_agents_and_is_deterministic(built_lib):
     assert ts1.opt_state["count"] == 6
 
 
+def test_cuda_graph_replay_matches_eager_enqueue(built_lib, monkeypatch):
+    """meta/graph.py: the captured-and-replayed meta-step (default) against the eager launch-by-launch step over 8
+    meta-steps that include agent re-creation by the sampler.  Same kernels, same order; the only arithmetic difference
+    is Adam's bias correction computed on the device (powf) instead of on the host."""
+    import to_ued_b200
+    monkeypatch.setattr(to_ued_b200, "CUDA_GRAPH", True)
+    hg, tg, _ = _run(steps=8)
+    monkeypatch.setattr(to_ued_b200, "CUDA_GRAPH", False)
+    he, te, _ = _run(steps=8)
+    assert tg.opt_state["count"] == te.opt_state["count"] == 8
+    for t, (a, b) in enumerate(zip(hg, he)):
+        for k in ("lpg_loss", "reg_lpg_loss", "value_loss", "lpg_agent_return"):
+            assert abs(float(a[k]) - float(b[k])) <= 1e-5 * max(1.0, abs(float(b[k]))), (t, k, float(a[k]), float(b[k]))
+    d = float((tg.params - te.params).abs().max() / te.params.abs().max())
+    assert d < 1e-6, f"graph vs eager LPG parameters differ by {d:.2e}"
+    assert float(hg[0]["lpg_loss"]) == float(he[0]["lpg_loss"])       # first step: eager warm-up call, bitwise equal
+
+
 def test_train_loop_frozen_and_es_paths(built_lib):
     h, ts, buf = _run(["--score_function", "frozen", "--buffer_size", "8"], steps=3)
     assert len(buf) == 8 and np.isfinite(float(h[-1]["lpg_loss"]))

@@ -15,6 +15,9 @@ NUM_STREAMS = int(os.environ.get("TOUED_NUM_STREAMS", "4"))
 # False: every kernel of a chunk runs on the chunk's own stream (no side streams for the token sort, the agent adjoint,
 # the embedding gradient and eval_agent) -- used by bench.py's per-kernel timing pass so that no launch has a neighbour
 SIDE_STREAMS = os.environ.get("TOUED_SIDE_STREAMS", "1") != "0"
+# True (default): make_lpg_train_step returns a step that is captured into a CUDA graph on its second call and replayed
+# afterwards (meta/graph.py; the states it returns alias static buffers).  "0": every call enqueues its launches eagerly.
+CUDA_GRAPH = os.environ.get("TOUED_CUDA_GRAPH", "1") != "0"
 # When a list: the meta-gradient step appends (label, chunk, timing-enabled CUDA event) at its phase boundaries
 # (tools/phase_timeline.py); None in production.
 PHASE_EVENTS = None

@@ -43,21 +43,25 @@ SIGNATURES = {
     "toued_sort_tokens": [_P] * 2 + [_I] * 3 + [_P],
     "toued_lpg_prepare": [_P] * 11 + [_I] * 6 + [_P],
     "toued_gru_forward": [_P] * 7 + [_I] * 5 + [_P],
-    "toued_agent_update": [_P] * 12 + [_I] * 4 + [_F] * 4 + [_P],
+    "toued_agent_update": [_P] * 12 + [_I] * 4 + [_F] * 4 + [_P, _P],
+    "toued_agent_scratch_floats": [_I] * 4,
     "toued_meta_loss": [_P] * 10 + [_I] * 5 + [_F] * 3 + [_I, _P],
-    "toued_agent_backward": [_P] * 14 + [_I] * 4 + [_F] * 9 + [_P],
+    "toued_agent_backward": [_P] * 14 + [_I] * 4 + [_F] * 9 + [_P, _P],
     "toued_transpose_wh": [_P] * 3,
     "toued_gru_backward": [_P] * 10 + [_I] * 4 + [_P],
     "toued_lpg_wgrad_workspace_floats": [],
     "toued_lpg_wgrad": [_P] * 11 + [_I] * 6 + [_P],
-    "toued_reduce_partials": [_P, _P, _I, _I, _P],
+    "toued_reduce_partials": [_P, _P, _I, _I, _I, _P],
+    "toued_lpg_wgrad_splits": [_I],
     "toued_lpg_wgrad_workspace_offset": [_I],
     "toued_lpg_wgrad_embed": [_P] * 6 + [_I] * 6 + [_P],
     "toued_pack_wh_backward": [_P] * 3,
     "toued_gru_backward_tc": [_P] * 11 + [_I] * 4 + [_P],
     "toued_wgrad_tc_splits": [],
+    "toued_wgrad_tc_small_splits": [],
     "toued_lpg_wgrad_tc": [_P] * 8 + [_I] * 4 + [_P],
     "toued_adam": [_P] * 4 + [_I, _I] + [_F] * 4 + [_P],
+    "toued_adam_dev": [_P] * 5 + [_I] + [_F] * 4 + [_P],
     "toued_get_nash": [_P] * 5 + [_I] * 4 + [_F, _P],
     "toued_projection_simplex": [_P, _I, _I, _P],
     "toued_es_ask": [_P, _P, _F, _P, _I, _I, _I, _P],
@@ -110,8 +114,10 @@ def stream_ptr():
 
 
 # kernels launched by one call of each entry point (for the bench's gpu_launches count)
-KERNELS_PER_CALL = {"toued_lpg_wgrad": 3, "toued_init_tables": 2, "toued_lpg_wgrad_tc": 2, "toued_pack_wh_forward": 2, "toued_pack_wh_forward_multi": 2}
+KERNELS_PER_CALL = {"toued_adam_dev": 2, "toued_lpg_wgrad": 3, "toued_init_tables": 2, "toued_lpg_wgrad_tc": 2, "toued_pack_wh_forward": 2, "toued_pack_wh_forward_multi": 2}
 LAUNCHES = {}          # entry point -> number of calls since reset_counters()
+GRAPH_KERNELS = [0]    # kernels launched by CUDA-graph replays since reset_counters() (meta/graph.py)
+ENV_STEPS = [0]        # gridworld env-steps simulated by the enqueued rollouts since reset_counters() (bench.py's metric)
 PROFILE = None         # when a dict: entry point -> list of (start, end) CUDA events
 
 
@@ -127,12 +133,14 @@ def h2d(t):
 def reset_counters(profile=False):
     global PROFILE
     H2D_BYTES[0] = 0
+    GRAPH_KERNELS[0] = 0
+    ENV_STEPS[0] = 0
     LAUNCHES.clear()
     PROFILE = {} if profile else None
 
 
 def kernel_launches():
-    return sum(n * KERNELS_PER_CALL.get(k, 1) for k, n in LAUNCHES.items())
+    return sum(n * KERNELS_PER_CALL.get(k, 1) for k, n in LAUNCHES.items()) + GRAPH_KERNELS[0]
 
 
 def profile_ms():
@@ -142,6 +150,10 @@ def profile_ms():
 
 def call(name, *args):
     LAUNCHES[name] = LAUNCHES.get(name, 0) + 1
+    if name == "toued_rollout":                      # (.., n_agents, n_workers, rollout_len, ..) at 10..12
+        ENV_STEPS[0] += args[10] * args[11] * args[12]
+    elif name == "toued_a2c_train":                  # (.., num_updates, n_agents, n_workers, rollout_len, ..) at 15..18
+        ENV_STEPS[0] += args[15] * args[16] * args[17] * args[18]
     if PROFILE is not None:
         import torch
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

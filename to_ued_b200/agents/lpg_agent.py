@@ -84,6 +84,8 @@ class Tape:
         self.scal_sum = torch.zeros((N, 8), dtype=f32, device=dev)
         self.step_in = torch.empty((ka, N), dtype=i32, device=dev)
         self.ep_return = torch.empty((N, W), dtype=f32, device=dev)
+        # run-sum scratch of toued_agent_update (one launch at a time per tape: the updates of a tape are sequential)
+        self.agent_scratch = torch.empty(_lib.lib().toued_agent_scratch_floats(N, W, L, D), dtype=f32, device=dev)
 
     def ti(self, k):       # table slot of theta_k
         return k if self.record else (k & 1)
@@ -152,7 +154,7 @@ def lpg_agent_train_step(k, tape: Tape, levels, step, lpg_params, lifetime_condi
     _lib.call("toued_agent_update", p(tape.obs[r]), p(tape.action[r]), p(tape.sorted_tok[r]), p(tape.pi_hat[a]),
               p(tape.y_hat[a]), p(tape.actor[t0]), p(tape.critic[t0]), p(tape.actor[t1]), p(tape.critic[t1]),
               p(levels), p(step), p(tape.scalars[a]), N, W, L, D, float(lr_actor), float(lr_critic),
-              float(max_grad_norm), float(agent_target_coeff), s)
+              float(max_grad_norm), float(agent_target_coeff), p(tape.agent_scratch), s)
     tape.scal_sum += tape.scalars[a]
 
 

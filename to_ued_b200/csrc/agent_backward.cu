@@ -442,22 +442,19 @@ extern "C" int toued_agent_backward(const int32_t* obs, const uint8_t* action, c
                                     float lr_actor, float lr_critic, float max_grad_norm,
                                     float agent_target_coeff, float policy_entropy_coeff,
                                     float target_entropy_coeff, float policy_l2_coeff, float target_l2_coeff,
-                                    float grad_scale, void* stream) {
+                                    float grad_scale, float* run_scratch, void* stream) {
     const int T = n_workers * rollout_len;
     TOUED_CHECK(n_agents > 0 && T > 0, "toued_agent_backward: empty problem");
+    TOUED_CHECK(run_scratch != nullptr, "toued_agent_backward: run_scratch (toued_agent_scratch_floats) is required");
     const size_t smem = sizeof(float) * ((size_t)T * 13 + 2 * 256 * 13) + seg_index_bytes(T);
     TOUED_CHECK(smem <= 200 * 1024, "toued_agent_backward: W*L=%d too large for shared memory", T);
     TOUED_CUDA(cudaFuncSetAttribute(agent_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TOUED_CUDA(cudaFuncSetAttribute(agent_backward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     cudaStream_t st = (cudaStream_t)stream;
-    float* run_scratch = nullptr;                       // stream-ordered: safe with concurrent chunks on other streams
-    if (int rc = toued_scratch_alloc((void**)&run_scratch, sizeof(float) * 13 * (size_t)(T < obs_dim ? T : obs_dim) * n_agents, st)) return rc;
     agent_backward_kernel<<<n_agents, 256, smem, st>>>(
         obs, action, sorted_tok, pi_hat, y_hat, actor_k, critic_k, actor_k1, critic_k1, update_scalars, lam, mu,
         d_pi_hat, d_y_hat, run_scratch, n_agents, n_workers, rollout_len, obs_dim, lr_actor, lr_critic, max_grad_norm,
         agent_target_coeff, policy_entropy_coeff, target_entropy_coeff, policy_l2_coeff, target_l2_coeff, grad_scale);
-    const cudaError_t launch_err = cudaGetLastError();
-    if (int rc = toued_scratch_free(run_scratch, st)) return rc;
-    TOUED_CUDA(launch_err);
+    TOUED_LAUNCH_CHECK();
     return 0;
 }

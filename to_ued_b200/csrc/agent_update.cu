@@ -176,7 +176,8 @@ extern "C" int toued_agent_update(const int32_t* obs, const uint8_t* action, con
                                   const float* critic_in, float* actor_out, float* critic_out,
                                   const void* levels, int32_t* step, float* scalars, int n_agents,
                                   int n_workers, int rollout_len, int obs_dim, float lr_actor,
-                                  float lr_critic, float max_grad_norm, float agent_target_coeff, void* stream) {
+                                  float lr_critic, float max_grad_norm, float agent_target_coeff, float* run_scratch,
+                                  void* stream) {
     const int T = n_workers * rollout_len;
     const size_t smem = agent_smem_bytes(T, obs_dim);
     TOUED_CHECK(n_agents > 0 && T > 0, "toued_agent_update: empty problem");
@@ -184,15 +185,20 @@ extern "C" int toued_agent_update(const int32_t* obs, const uint8_t* action, con
     TOUED_CHECK(actor_in != actor_out && critic_in != critic_out, "toued_agent_update: in-place update not supported");
     TOUED_CUDA(cudaFuncSetAttribute(agent_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TOUED_CUDA(cudaFuncSetAttribute(agent_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    TOUED_CHECK(run_scratch != nullptr, "toued_agent_update: run_scratch (toued_agent_scratch_floats) is required");
     cudaStream_t st = (cudaStream_t)stream;
-    float* run_scratch = nullptr;                       // stream-ordered: safe with concurrent chunks on other streams
-    if (int rc = toued_scratch_alloc((void**)&run_scratch, sizeof(float) * 13 * (size_t)(T < obs_dim ? T : obs_dim) * n_agents, st)) return rc;
     agent_update_kernel<<<n_agents, 256, smem, st>>>(
         obs, action, sorted_tok, pi_hat, y_hat, actor_in, critic_in, actor_out, critic_out,
         (const LevelRec*)levels, step, scalars, run_scratch, n_agents, n_workers, rollout_len, obs_dim,
         lr_actor, lr_critic, max_grad_norm, agent_target_coeff);
-    const cudaError_t launch_err = cudaGetLastError();
-    if (int rc = toued_scratch_free(run_scratch, st)) return rc;
-    TOUED_CUDA(launch_err);
+    TOUED_LAUNCH_CHECK();
     return 0;
+}
+
+// floats of caller-provided scratch for one toued_agent_update / toued_agent_backward launch: the per-row run sums
+// [min(W*L, D)][13] of every agent (written and read inside the launch only; L2-resident)
+extern "C" int toued_agent_scratch_floats(int n_agents, int n_workers, int rollout_len, int obs_dim) {
+    const long long T = (long long)n_workers * rollout_len;
+    const long long n = 13ll * (T < obs_dim ? T : obs_dim) * n_agents;
+    return n < (1ll << 31) ? (int)n : -1;
 }

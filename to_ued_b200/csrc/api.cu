@@ -15,37 +15,6 @@ void toued_set_error(const char* fmt, ...) {
 
 extern "C" const char* toued_last_error(void) { return g_err; }
 
-// Stream-ordered scratch for kernels whose temporaries do not fit shared memory: one private pool per device that
-// keeps its memory across synchronisations (release threshold = max; the default pool would hand it back to the
-// driver at every synchronisation and re-allocate on the next call).
-#include <mutex>
-static cudaMemPool_t g_pools[64] = {};
-static std::mutex g_pool_mutex;
-
-int toued_scratch_alloc(void** ptr, size_t bytes, cudaStream_t st) {
-    int dev = 0;
-    TOUED_CUDA(cudaGetDevice(&dev));
-    TOUED_CHECK(dev >= 0 && dev < 64, "toued_scratch_alloc: device index %d out of range", dev);
-    {
-        std::lock_guard<std::mutex> lock(g_pool_mutex);
-        if (!g_pools[dev]) {
-            cudaMemPoolProps props = {};
-            props.allocType = cudaMemAllocationTypePinned;
-            props.location.type = cudaMemLocationTypeDevice;
-            props.location.id = dev;
-            TOUED_CUDA(cudaMemPoolCreate(&g_pools[dev], &props));
-            uint64_t keep = UINT64_MAX;
-            TOUED_CUDA(cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
-        }
-    }
-    TOUED_CUDA(cudaMallocFromPoolAsync(ptr, bytes, g_pools[dev], st));
-    return 0;
-}
-
-int toued_scratch_free(void* ptr, cudaStream_t st) {
-    TOUED_CUDA(cudaFreeAsync(ptr, st));
-    return 0;
-}
 extern "C" int toued_version(void) { return 1; }
 
 // Host-side key plumbing (no GPU involved): out[i][0..n) = threefry_2x32(keys[i], iota(n)) with jax 0.4.13's

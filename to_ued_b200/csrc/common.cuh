@@ -232,6 +232,3 @@ void toued_set_error(const char* fmt, ...);
 #define TOUED_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     toued_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); return 2; } } while (0)
 #define TOUED_LAUNCH_CHECK() TOUED_CUDA(cudaGetLastError())
-// stream-ordered scratch from the library's own memory pool (api.cu); both return 0 or an error code with the message set
-int toued_scratch_alloc(void** ptr, size_t bytes, cudaStream_t st);
-int toued_scratch_free(void* ptr, cudaStream_t st);

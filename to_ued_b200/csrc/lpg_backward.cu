@@ -461,7 +461,8 @@ embed_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
     }
 }
 
-constexpr int WG_SPLITS = 37;        // token splits of the dWh GEMM (SIMT uses 32 of them, the tensor-core kernel 37)
+constexpr int WG_SPLITS = 37;        // capacity of the dWh partial area in token splits (SIMT kernel: 32, tensor-core kernel:
+                                     // toued_wgrad_tc_splits() = 24; both checked against this capacity)
 constexpr int WG_SPLITS_SIMT = 32;
 constexpr int SM_SPLITS = 592;       // 4 per SM for the streaming kernels
 constexpr int EM_SPLITS = 296;
@@ -536,6 +537,9 @@ __global__ void reduce_partials_kernel(const float* __restrict__ ws, float* __re
     }
 }
 
+// split counts of the SIMT weight-gradient kernels: which = 0 -> dWh areas, 1 -> small-parameter areas
+extern "C" int toued_lpg_wgrad_splits(int which) { return which == 0 ? WG_SPLITS_SIMT : SM_SPLITS; }
+
 // offsets (in floats) of the three partial areas inside the workspace: {Wh, small, embed}
 extern "C" int toued_lpg_wgrad_workspace_offset(int which) {
     if (which == 0) return 0;
@@ -556,11 +560,13 @@ extern "C" int toued_lpg_wgrad_embed(const int32_t* obs, const uint8_t* done, co
     return 0;
 }
 
-extern "C" int toued_reduce_partials(const float* workspace, float* grad, int lifetime_conditioning, int wh_splits, void* stream) {
+extern "C" int toued_reduce_partials(const float* workspace, float* grad, int lifetime_conditioning, int wh_splits,
+                                     int sm_splits, void* stream) {
     const int n = LPG_H * LPG_G + SM_TOTAL + EM_TOTAL;
+    // the producer says how many partial areas it filled (SIMT path: toued_lpg_wgrad_splits(); tensor-core path:
+    // toued_wgrad_tc_splits() / toued_wgrad_tc_small_splits()); areas beyond that are never read
     TOUED_CHECK(wh_splits >= 1 && wh_splits <= WG_SPLITS, "toued_reduce_partials: wh_splits=%d out of range", wh_splits);
-    // SIMT path: 32 Wh splits / 592 small splits; tensor-core path: 24 / 148
-    const int sm_splits = wh_splits == WG_SPLITS_SIMT ? SM_SPLITS : 148;
+    TOUED_CHECK(sm_splits >= 1 && sm_splits <= SM_SPLITS, "toued_reduce_partials: sm_splits=%d out of range", sm_splits);
     reduce_partials_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, grad, lifetime_conditioning ? 7 : 5, wh_splits, sm_splits);
     TOUED_LAUNCH_CHECK();
     return 0;
@@ -585,6 +591,33 @@ extern "C" int toued_adam(float* params, const float* grad, float* mu, float* nu
     TOUED_CHECK(n > 0 && count >= 1, "toued_adam: bad arguments");
     const float c1 = 1.0f - powf(b1, (float)count), c2 = 1.0f - powf(b2, (float)count);
     adam_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params, grad, mu, nu, n, lr, b1, b2, eps, c1, c2);
+    TOUED_LAUNCH_CHECK();
+    return 0;
+}
+
+// Same step with the 1-based update count kept on the device (count_dev holds the number of updates done so far and is
+// incremented after the step): nothing of the call depends on host state, so it can sit inside a captured CUDA graph.
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, const int* __restrict__ count_dev, int n, float lr, float b1,
+                                float b2, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float cnt = (float)(*count_dev + 1);
+    const float c1 = 1.0f - powf(b1, cnt), c2 = 1.0f - powf(b2, cnt);
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= lr * (mi / c1) / (sqrtf(vi / c2) + eps);
+}
+__global__ void count_incr_kernel(int* count_dev) { *count_dev += 1; }
+
+extern "C" int toued_adam_dev(float* params, const float* grad, float* mu, float* nu, int* count_dev, int n, float lr,
+                              float b1, float b2, float eps, void* stream) {
+    TOUED_CHECK(n > 0 && count_dev != nullptr, "toued_adam_dev: bad arguments");
+    adam_dev_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params, grad, mu, nu, count_dev, n, lr, b1, b2, eps);
+    TOUED_LAUNCH_CHECK();
+    count_incr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(count_dev);
     TOUED_LAUNCH_CHECK();
     return 0;
 }

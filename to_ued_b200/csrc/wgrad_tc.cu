@@ -461,7 +461,9 @@ wgrad_heads_mma_kernel(const __half* __restrict__ h16, const float* __restrict__
 
 constexpr int WT_SPLITS = 24;              // 6 tile types x 24 = 144 CTAs
 
+static_assert(WT_SPLITS <= 37 && HT_SPLITS <= 592, "partial areas of toued_lpg_wgrad_workspace_floats (lpg_backward.cu) are sized for 37 / 592 splits");
 extern "C" int toued_wgrad_tc_splits(void) { return WT_SPLITS; }
+extern "C" int toued_wgrad_tc_small_splits(void) { return HT_SPLITS; }
 
 extern "C" int toued_lpg_wgrad_tc(const void* hpimg, const void* dgimg, const void* ximg, const void* h16,
                                   const float* d_pi_hat, const float* dl, float* wh_partials, float* small_partials,

@@ -63,7 +63,8 @@ def _train_state_arrays(train_state) -> dict:
     out["params"] = _np(train_state.params)
     out["step"] = np.asarray(int(train_state.step))
     for k, v in train_state.opt_state.items():
-        out[f"opt_state/{k}"] = _np(v)
+        if not k.endswith("_dev"):                          # device mirror of `count` kept by the graphed step
+            out[f"opt_state/{k}"] = _np(v)
     return out
 
 

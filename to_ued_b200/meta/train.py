@@ -63,6 +63,8 @@ class MetaGradWorkspace:
         self.whT = torch.empty((768, 256), dtype=f32, device=device)
         self.partials = torch.empty(_lib.lib().toued_lpg_wgrad_workspace_floats(), dtype=f32, device=device)
         self.loss_scal = torch.empty((N, 2), dtype=f32, device=device)
+        # run-sum scratch of toued_agent_backward (its launches of one chunk are sequential on the agent stream)
+        self.ab_scratch = torch.empty(_lib.lib().toued_agent_scratch_floats(N, W, L, obs_dim), dtype=f32, device=device)
         if self.tape.precision == "tc":
             Rp = (R + 63) // 64 * 64
             self.whb_img = torch.empty(256 * 768, dtype=torch.bfloat16, device=device)
@@ -113,10 +115,16 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                              rollout_manager, num_mini_batches: int, gamma: float, gae_lambda: float,
                              lpg_hypers: LpgHyperparams, *, outer_product_quirk: bool = True,
                              global_agent_offset: int = 0, global_num_agents: Optional[int] = None,
-                             eval_workers: int = 4, return_grad: bool = False, num_streams: Optional[int] = None):
+                             eval_workers: int = 4, return_grad: bool = False, num_streams: Optional[int] = None,
+                             _static: Optional[dict] = None):
     """Update a batch of agents with LPG, then update LPG with the regularised final agent loss
-    (meta/train.py:14-130).  rng: the step key (uint32[2]).  Returns
-    (lpg_train_state, agent_states, value_critic_states, metrics)."""
+    (meta/train.py:14-130).  rng: the step key (uint32[2], or an int32[1, 2] device tensor).  Returns
+    (lpg_train_state, agent_states, value_critic_states, metrics).
+
+    ``_static`` (used by meta/graph.py when the step is captured into a CUDA graph): the per-agent outputs are written
+    into the given buffers (which may be the input buffers: every chunk reads its slice before it writes it), Adam runs
+    in place on the LPG parameters with its update count in device memory, and the metric vector is returned as one
+    tensor -- nothing in the enqueued work then depends on host state."""
     env = rollout_manager.env
     actor, critic = agent_states.actor_state, agent_states.critic_state
     N, W = agent_states.env_state.packed.shape
@@ -154,11 +162,14 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     gscale = 1.0 / n_global
     bK = [c / K for c in (lpg_hypers.policy_entropy_coeff, lpg_hypers.target_entropy_coeff,
                           lpg_hypers.policy_l2_coeff, lpg_hypers.target_l2_coeff)]
-    new_actor = torch.empty_like(actor.params)
-    new_critic = torch.empty_like(critic.params)
-    new_step = torch.empty_like(actor.step)
-    new_state = torch.empty_like(agent_states.env_state.packed)
-    new_obs = torch.empty_like(agent_states.env_obs)
+    if _static is not None:
+        new_actor, new_critic, new_step, new_state, new_obs = _static["out"]
+    else:
+        new_actor = torch.empty_like(actor.params)
+        new_critic = torch.empty_like(critic.params)
+        new_step = torch.empty_like(actor.step)
+        new_state = torch.empty_like(agent_states.env_state.packed)
+        new_obs = torch.empty_like(agent_states.env_obs)
     msums = [torch.zeros(8, dtype=torch.float32, device=dev) for _ in range(S)]
     returns = torch.empty(N, dtype=torch.float32, device=dev)
     ready = torch.cuda.Event()
@@ -270,7 +281,7 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                   p(tape.actor[k + 1]), p(tape.critic[k + 1]), p(tape.scalars[k]), p(ws.lam), p(ws.mu),
                   p(ws.d_pi_hat2[buf]), p(ws.d_y_hat2[buf]), nb, W, L, D, float(actor.learning_rate),
                   float(critic.learning_rate), float(actor.max_grad_norm),
-                  float(lpg_hypers.agent_target_coeff), *[float(b) for b in bK], float(gscale), s)
+                  float(lpg_hypers.agent_target_coeff), *[float(b) for b in bK], float(gscale), p(ws.ab_scratch), s)
 
     def backward_step(mb, k):
         """Reverse pass of update k.  Tensor-core path: three streams per chunk --
@@ -373,30 +384,41 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     msum = msums[0] if S == 1 else torch.stack(msums).sum(0)
 
     grad = torch.empty(P, dtype=torch.float32, device=dev)
-    n_wh = _lib.lib().toued_wgrad_tc_splits() if tc else 32
-    _lib.call("toued_reduce_partials", p(wss[0].partials), p(grad), cond, n_wh, s)
+    L_ = _lib.lib()
+    n_wh, n_sm = (L_.toued_wgrad_tc_splits(), L_.toued_wgrad_tc_small_splits()) if tc else \
+        (L_.toued_lpg_wgrad_splits(0), L_.toued_lpg_wgrad_splits(1))
+    _lib.call("toued_reduce_partials", p(wss[0].partials), p(grad), cond, n_wh, n_sm, s)
     for ws in wss[1:min(S, num_mini_batches)]:
         g2 = torch.empty_like(grad)
-        _lib.call("toued_reduce_partials", p(ws.partials), p(g2), cond, n_wh, s)
+        _lib.call("toued_reduce_partials", p(ws.partials), p(g2), cond, n_wh, n_sm, s)
         grad += g2
-    mvec = torch.cat([msum, returns.sum().view(1)])
+    # one collective for the gradient AND the 9 metric sums: they travel in the same buffer
+    red = torch.cat([grad, msum, returns.sum().view(1)])
     if dist is not None:
-        dist.all_reduce(grad)                     # sum of per-rank (1/n_global)-scaled sums = mean
-        dist.all_reduce(mvec)
-    mvec = mvec / n_global
+        dist.all_reduce(red)                      # sum of per-rank (1/n_global)-scaled sums = mean
+    grad, mvec = red[:P], red[P:] / n_global
     # ---- Adam on the LPG parameters (meta/train.py:129) ----
-    new_params = lpg.clone()
-    opt_state = lpg_train_state.tx.update_(new_params, grad, {**lpg_train_state.opt_state,
-                                                              "mu": lpg_train_state.opt_state["mu"].clone(),
-                                                              "nu": lpg_train_state.opt_state["nu"].clone()})
-    new_lpg = lpg_train_state.replace(params=new_params, opt_state=opt_state, step=lpg_train_state.step + 1)
+    if _static is not None:
+        ost = lpg_train_state.opt_state
+        lpg_train_state.tx.update_dev_(lpg, grad, ost["mu"], ost["nu"], _static["count_dev"])
+        new_lpg = lpg_train_state
+    else:
+        new_params = lpg.clone()
+        opt_state = lpg_train_state.tx.update_(new_params, grad, {**lpg_train_state.opt_state,
+                                                                  "mu": lpg_train_state.opt_state["mu"].clone(),
+                                                                  "nu": lpg_train_state.opt_state["nu"].clone()})
+        new_lpg = lpg_train_state.replace(params=new_params, opt_state=opt_state, step=lpg_train_state.step + 1)
     agent_out = agent_states.replace(
         actor_state=actor.replace(params=new_actor, step=new_step),
-        critic_state=critic.replace(params=new_critic, step=new_step.clone()),
+        critic_state=critic.replace(params=new_critic, step=new_step if _static is not None else new_step.clone()),
         env_obs=new_obs, env_state=EnvState(new_state, env.max_n_objs),
         host_step=_advance_host_step(agent_states.host_step, agent_states.level.lifetime, K))
     # value critic: parameters untouched (Q2); its step counter advances K + 1 per meta-step
-    value_out = value_critic_states.replace(step=value_critic_states.step + (K + 1))
+    if _static is not None:
+        value_critic_states.step.add_(K + 1)
+        value_out = value_critic_states
+    else:
+        value_out = value_critic_states.replace(step=value_critic_states.step + (K + 1))
     metrics = {
         "lpg_loss": mvec[0], "reg_lpg_loss": mvec[1], "value_loss": mvec[2],
         "lpg_agent": {"policy_l2": mvec[3], "policy_entropy": mvec[4], "critic_loss": mvec[5],
@@ -405,6 +427,8 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     }
     if return_grad:
         metrics["_grad"] = grad
+    if _static is not None:
+        metrics["_mvec"] = mvec
     _phase("end", -1, main)
     return new_lpg, agent_out, value_out, metrics
 

@@ -37,6 +37,14 @@ class Adam:
                   _lib.stream_ptr())
         return {"mu": state["mu"], "nu": state["nu"], "count": count}
 
+    def update_dev_(self, params: torch.Tensor, grad: torch.Tensor, mu: torch.Tensor, nu: torch.Tensor,
+                    count_dev: torch.Tensor) -> None:
+        """The same step with the update count in device memory (int32[1], incremented by the call): capturable in a
+        CUDA graph (meta/graph.py)."""
+        _lib.call("toued_adam_dev", _lib.ptr(params), _lib.ptr(grad), _lib.ptr(mu), _lib.ptr(nu), _lib.ptr(count_dev),
+                  params.numel(), float(self.learning_rate), float(self.b1), float(self.b2), float(self.eps),
+                  _lib.stream_ptr())
+
 
 def create_optimizer(optimizer: str, learning_rate: float, max_grad_norm: float):
     if optimizer == "SGD":
