@@ -321,8 +321,15 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int u = u0 + e;
-                    rr[e] = sigmoid_fast(ar[e]);                          // input projection + bias already inside
-                    zz[e] = sigmoid_fast(az[e]);
+                    // The epilogue is bound by the MUFU pipe (16 results / clk / SM; 6 MUFU operations per unit with three
+                    // ex2 + rcp activations).  The two sigmoids share ONE reciprocal: inv = 1/(a b), r = b inv, z = a inv
+                    // (exponents clamped at 60 so that the product stays finite; sigmoid is 0 to fp32 there anyway).
+                    const float ea = ex2_approx(fminf(-1.4426950408889634f * ar[e], 60.0f));
+                    const float eb = ex2_approx(fminf(-1.4426950408889634f * az[e], 60.0f));
+                    const float da = 1.0f + ea, db = 1.0f + eb;
+                    const float inv = rcp_approx(da * db);
+                    rr[e] = inv * db;                                     // input projection + bias already inside
+                    zz[e] = inv * da;
                     hn[e] = an[e] + sbhn[u];
                     nn[e] = tanh_fast(ai[e] + rr[e] * hn[e]);
                     hv[e] = (1.0f - zz[e]) * nn[e] + zz[e] * hp[e];

@@ -57,7 +57,8 @@ class MetaGradWorkspace:
         self.d_y_hat2 = [torch.empty((L, R, 8), dtype=f32, device=device) for _ in range(2)]
         self.dx2 = [torch.empty((L, R, 2), dtype=f32, device=device) for _ in range(2)]
         self.d_pi_hat, self.d_y_hat, self.dx = self.d_pi_hat2[0], self.d_y_hat2[0], self.dx2[0]
-        self.dl = torch.empty((L, R, 8), dtype=f32, device=device)
+        self.dl2 = [torch.empty((L, R, 8), dtype=f32, device=device) for _ in range(2)]
+        self.dl = self.dl2[0]
         self.lam = torch.empty((N, obs_dim, 8), dtype=f32, device=device)
         self.mu = torch.empty((N, obs_dim, 8), dtype=f32, device=device)
         self.whT = torch.empty((768, 256), dtype=f32, device=device)
@@ -69,7 +70,10 @@ class MetaGradWorkspace:
             Rp = (R + 63) // 64 * 64
             self.whb_img = torch.empty(256 * 768, dtype=torch.bfloat16, device=device)
             # bf16 token-tile image of (dar, daz, dhn, dan): 16 column groups of 64
-            self.dgimg = torch.zeros(L * Rp * 1024 * 2, dtype=torch.uint8, device=device)
+            # (double-buffered over the update index like the cotangents: the weight-gradient GEMMs of update k run on
+            #  their own stream next to the BPTT of update k-1)
+            self.dgimg2 = [torch.zeros(L * Rp * 1024 * 2, dtype=torch.uint8, device=device) for _ in range(2)]
+            self.dgimg = self.dgimg2[0]
         self.off_small = _lib.lib().toued_lpg_wgrad_workspace_offset(1)
         self.key = (N, W, L, obs_dim, K, n_params, str(device))
 
@@ -184,11 +188,12 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
     eval_done = [None] * S
     eval_stream = _side_streams(dev, S + 1)[S] if S > 1 else _eval_stream(dev)
     # per chunk: a stream for the agent adjoints and one for the embedding gradients of the reverse pass
-    pool = _side_streams(dev, 4 * S + 1)
+    pool = _side_streams(dev, 5 * S + 1)
     ab_streams, em_streams = pool[S + 1:2 * S + 1], pool[2 * S + 1:3 * S + 1]
     ev_streams = [eval_stream] + pool[3 * S + 1:4 * S]          # one evaluation stream per chunk
+    wg_streams = pool[4 * S + 1:5 * S + 1]                      # weight-gradient GEMMs of the tensor-core reverse pass
     if not to_ued_b200.SIDE_STREAMS:                            # per-kernel timing mode: everything on the chunk's stream
-        ab_streams = em_streams = ev_streams = list(streams)
+        ab_streams = em_streams = ev_streams = wg_streams = list(streams)
     evs = {}
 
     # The host enqueues the chains of a group of S mini-batches round-robin, one agent update at a time (forward:
@@ -320,14 +325,18 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
             st.wait_event(ev["ab"][k])
             if k + 2 <= K - 1:
                 st.wait_event(ev["em"][k + 2])              # dx [k & 1] has been consumed
+                st.wait_event(ev["wg"][k + 2])              # ... and so have the dG image and dl [k & 1]
             _lib.call("toued_gru_backward_tc", p(tape.done[k]), p(lpg), p(ws.whb_img), p(tape.h16[k]),
-                      p(tape.fac[k]), p(tape.y_hat[k]), p(ws.d_pi_hat2[buf]), p(ws.d_y_hat2[buf]), p(ws.dgimg), p(ws.dl),
+                      p(tape.fac[k]), p(tape.y_hat[k]), p(ws.d_pi_hat2[buf]), p(ws.d_y_hat2[buf]), p(ws.dgimg2[buf]), p(ws.dl2[buf]),
                       p(ws.dx2[buf]), nb, W, L, cond, s)
             ev["bwd"][k].record(st)
             _phase(f"bwd{k}", mb, st)
-            _lib.call("toued_lpg_wgrad_tc", p(tape.hpimg[k]), p(ws.dgimg), p(tape.ximg[k]), p(tape.h16[k]),
-                      p(ws.d_pi_hat2[buf]), p(ws.dl), p(ws.partials), p(ws.partials[ws.off_small:]),
-                      nb, W, L, 0 if first else 1, s)
+        with torch.cuda.stream(wg_streams[slot]):
+            st = wg_streams[slot]
+            st.wait_event(ev["bwd"][k])
+            _lib.call("toued_lpg_wgrad_tc", p(tape.hpimg[k]), p(ws.dgimg2[buf]), p(tape.ximg[k]), p(tape.h16[k]),
+                      p(ws.d_pi_hat2[buf]), p(ws.dl2[buf]), p(ws.partials), p(ws.partials[ws.off_small:]),
+                      nb, W, L, 0 if first else 1, _lib.stream_ptr())
             ev["wg"][k].record(st)
             _phase(f"wgrad{k}", mb, st)
         with torch.cuda.stream(em_streams[slot]):
@@ -345,6 +354,7 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
             ev = evs.pop(mb)
             if ev["em"]:
                 streams[slot].wait_event(ev["em"][0])          # joins the embed stream (the agent stream is already joined)
+                streams[slot].wait_event(ev["wg"][0])          # ... and the weight-gradient stream
             # ---- metrics (sums over agents; divided by n_global after the all-reduce) ----
             lpg_loss, value_loss = ws.loss_scal[:, 0], ws.loss_scal[:, 1]
             reg = (lpg_loss - lpg_hypers.policy_entropy_coeff * am.policy_entropy + lpg_hypers.policy_l2_coeff * am.policy_l2
