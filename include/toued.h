@@ -145,8 +145,8 @@ int toued_lpg_wgrad(const int32_t* obs, const uint8_t* done, const float* critic
                     int lifetime_conditioning, int accumulate, void* stream);
 int toued_lpg_wgrad_workspace_offset(int which);   /* float offset of the {0: Wh, 1: small, 2: embed} partial area */
 int toued_lpg_wgrad_embed(const int32_t* obs, const uint8_t* done, const float* critic, const float* lpg_params,
-                          const float* dx, float* workspace, int n_agents, int n_workers, int rollout_len,
-                          int obs_dim, int lifetime_conditioning, int accumulate, void* stream);
+                          const float* dx, float* workspace, const uint32_t* cotangent_max, int n_agents, int n_workers,
+                          int rollout_len, int obs_dim, int lifetime_conditioning, int accumulate, void* stream);
 /* wh_splits / sm_splits: how many dWh and small-parameter partial areas the producer filled --
  * toued_lpg_wgrad_splits(0) / (1) after toued_lpg_wgrad, toued_wgrad_tc_splits() / toued_wgrad_tc_small_splits() after
  * toued_lpg_wgrad_tc.  Areas beyond these counts are never read.                                         */
@@ -277,20 +277,27 @@ int toued_gru_forward_tc_multi(const float* x, const uint8_t* done, const float*
 
 /* Pack Wh into the bf16 SW128 chunk images of the tensor-core reverse pass (384 KiB).               */
 int toued_pack_wh_backward(const float* lpg_params, void* whb_img, void* stream);
-/* Tensor-core BPTT (reverse of toued_gru_forward_tc).  Reads h16 / fac saved by the forward; writes
- *   dgimg bf16 token-tile image [L*Rp/64][16][64][64]: column groups 0-3 dar, 4-7 daz, 8-11 dhn, 12-15 dan
+/* Scaled fp16 reverse pass.  The reverse pass is linear in the cotangents (d_pi_hat, d_y_hat), which are far below
+ * fp16's range: toued_cotangent_max writes max |cotangent| of a launch (bit pattern of a float) to cotangent_max u32[1],
+ * the tensor-core reverse kernels derive a power of two S from it, run on S x cotangents with fp16 operands (saturating
+ * conversions) and fp32 accumulation, and the consumers divide S back out.  cotangent_max == NULL means S = 1.    */
+int toued_cotangent_max(const float* d_pi_hat, const float* d_y_hat, int n_agents, int n_workers, int rollout_len,
+                        uint32_t* cotangent_max, void* stream);
+/* Tensor-core BPTT (reverse of toued_gru_forward_tc).  Reads h16 / fac saved by the forward; writes, in units of S,
+ *   dgimg fp16 token-tile image [L*Rp/64][16][64][64]: column groups 0-3 dar, 4-7 daz, 8-11 dhn, 12-15 dan
  *   dl f32[L][R][8] head-logit cotangents, dx f32[L][R][2] (d pyt, d pyt1)                          */
 int toued_gru_backward_tc(const uint8_t* done, const float* lpg_params, const void* whb_img,
                           const void* h16, const void* fac, const float* y_hat, const float* d_pi_hat,
-                          const float* d_y_hat, void* dgimg, float* dl, float* dx, int n_agents,
-                          int n_workers, int rollout_len, int lifetime_conditioning, void* stream);
+                          const float* d_y_hat, void* dgimg, float* dl, float* dx, const uint32_t* cotangent_max,
+                          int n_agents, int n_workers, int rollout_len, int lifetime_conditioning, void* stream);
 /* Tensor-core weight gradients from the token tile images (hpimg from the forward, dgimg from the
  * backward) + streaming small gradients; partial areas of the toued_lpg_wgrad workspace.             */
 int toued_wgrad_tc_splits(void);
 int toued_wgrad_tc_small_splits(void);
 int toued_lpg_wgrad_tc(const void* hpimg, const void* dgimg, const void* ximg, const void* h16,
                        const float* d_pi_hat, const float* dl, float* wh_partials, float* small_partials,
-                       int n_agents, int n_workers, int rollout_len, int accumulate, void* stream);
+                       const uint32_t* cotangent_max, int n_agents, int n_workers, int rollout_len, int accumulate,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -115,13 +115,13 @@ def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond, n):
 
 
 def _unpack_tile_img(img_u8, n_tok, C):
-    """token tile image (uint8 tensor) -> bf16 [n_tok][C] (inverse of tile_img_offset in csrc/tc.cuh)."""
+    """token tile image (uint8 tensor) -> fp16 [n_tok][C] (inverse of tile_img_offset in csrc/tc.cuh)."""
     tok = torch.arange(n_tok, device=img_u8.device)
     col = torch.arange(C, device=img_u8.device)
     tb, r = tok // 64, tok % 64
     cg, cin = col // 64, col % 64
     off = ((tb[:, None] * (C // 64) + cg[None, :]) << 13) + r[:, None] * 128 + (((cin[None, :] >> 3) ^ (r[:, None] & 7)) << 4) + ((cin[None, :] & 7) << 1)
-    flat = img_u8.view(torch.bfloat16)
+    flat = img_u8.view(torch.float16)
     return flat[(off // 2).reshape(-1)].reshape(n_tok, C)
 
 

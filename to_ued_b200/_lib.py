@@ -54,12 +54,13 @@ SIGNATURES = {
     "toued_reduce_partials": [_P, _P, _I, _I, _I, _P],
     "toued_lpg_wgrad_splits": [_I],
     "toued_lpg_wgrad_workspace_offset": [_I],
-    "toued_lpg_wgrad_embed": [_P] * 6 + [_I] * 6 + [_P],
+    "toued_lpg_wgrad_embed": [_P] * 7 + [_I] * 6 + [_P],
+    "toued_cotangent_max": [_P, _P, _I, _I, _I, _P, _P],
     "toued_pack_wh_backward": [_P] * 3,
-    "toued_gru_backward_tc": [_P] * 11 + [_I] * 4 + [_P],
+    "toued_gru_backward_tc": [_P] * 12 + [_I] * 4 + [_P],
     "toued_wgrad_tc_splits": [],
     "toued_wgrad_tc_small_splits": [],
-    "toued_lpg_wgrad_tc": [_P] * 8 + [_I] * 4 + [_P],
+    "toued_lpg_wgrad_tc": [_P] * 9 + [_I] * 4 + [_P],
     "toued_adam": [_P] * 4 + [_I, _I] + [_F] * 4 + [_P],
     "toued_adam_dev": [_P] * 5 + [_I] + [_F] * 4 + [_P],
     "toued_get_nash": [_P] * 5 + [_I] * 4 + [_F, _P],

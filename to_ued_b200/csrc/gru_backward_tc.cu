@@ -6,12 +6,16 @@
 //     dG_g   = dh_t * f_g            (f_r, f_z, f_hn, f_an saved by the forward epilogue)
 //     carry' = dGh @ Wh^T + z * dh_t
 // The carry stays in fp32 in TMEM (two 256-column sets, ping-pong): dGh @ Wh^T is accumulated by
-// tcgen05.mma from bf16 operands (dG written by the epilogue warps into SW128 smem chunks, Wh chunks
+// tcgen05.mma from fp16 operands (dG written by the epilogue warps into SW128 smem chunks, Wh chunks
 // streamed by a TMA-producer warp), and the element-wise z*dh_t term is injected into the same
-// accumulator by a tiny identity MMA on a bf16 hi/lo pair, so the recurrent chain keeps ~16 mantissa
+// accumulator by a tiny identity MMA on an fp16 hi/lo pair, so the recurrent chain keeps ~22 mantissa
 // bits without ever leaving tensor memory.
-// Outputs for the weight-gradient kernels: dG (dar, daz, dhn, dan) as a bf16 token-tile image,
-// the head-logit cotangents dl and d pyt / d pyt1.
+// Scaled arithmetic (tc.cuh, "scaled fp16 operands"): the kernel multiplies the incoming cotangents by the power of two
+// S derived from `cotmax` and everything downstream -- carry, dG, dl, dx -- is in units of S; the consumers
+// (toued_lpg_wgrad_tc, toued_lpg_wgrad_embed) take S back out.  Round 1 used bf16 operands (8 significant bits; the
+// rounding of Wh is systematic over all tokens) and left 0.6-1.6e-2 of error on the GRU weight blocks of the meta-gradient.
+// Outputs for the weight-gradient kernels: S * dG (dar, daz, dhn, dan) as an fp16 token-tile image,
+// the head-logit cotangents S * dl and S * (d pyt, d pyt1).
 #include "tc.cuh"
 #include "lpg_common.cuh"
 #include "../../include/toued.h"
@@ -24,18 +28,18 @@ constexpr int BT_BCHUNK = LPG_H * 128;           // 32 KB: [256 units][64 c]
 constexpr int BT_NSB = 3;
 constexpr int BT_ICHUNK = 64 * 128;              // 8 KB identity
 
-// Wh[j][c] -> 12 bf16 K-major SW128 chunk images [cc = c / 64][row j][k = c % 64]
-__global__ void pack_wh_bwd_kernel(const float* __restrict__ Wh, __nv_bfloat16* __restrict__ img) {
+// Wh[j][c] -> 12 fp16 K-major SW128 chunk images [cc = c / 64][row j][k = c % 64]
+__global__ void pack_wh_bwd_kernel(const float* __restrict__ Wh, __half* __restrict__ img) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= LPG_H * LPG_G) return;
     const int j = i / LPG_G, c = i % LPG_G;
     char* base = reinterpret_cast<char*>(img) + (size_t)(c >> 6) * BT_BCHUNK;
-    *reinterpret_cast<__nv_bfloat16*>(base + sw128_offset(LPG_H, j, c & 63)) = __float2bfloat16_rn(Wh[i]);
+    *reinterpret_cast<__half*>(base + sw128_offset(LPG_H, j, c & 63)) = __float2half_rn(Wh[i]);
 }
 
 extern "C" int toued_pack_wh_backward(const float* lpg_params, void* whb_img, void* stream) {
     pack_wh_bwd_kernel<<<(LPG_H * LPG_G + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        lpg_params + lpg_offsets(5).Wh, (__nv_bfloat16*)whb_img);
+        lpg_params + lpg_offsets(5).Wh, (__half*)whb_img);
     TOUED_LAUNCH_CHECK();
     return 0;
 }
@@ -45,22 +49,13 @@ __device__ __forceinline__ void unpack8h(const uint4& r, float (&v)[8]) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
 }
-__device__ __forceinline__ uint4 pack8bf(const float (&v)[8]) {
-    uint4 r;
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
-    r.x = *reinterpret_cast<uint32_t*>(&h0); r.y = *reinterpret_cast<uint32_t*>(&h1);
-    r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
-    return r;
-}
-
 __global__ void __launch_bounds__(BT_THREADS, 1)
 gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict__ lpg, int X,
                        const unsigned char* __restrict__ whb_img, const __half* __restrict__ h16,
                        const __half* __restrict__ fac, const float* __restrict__ y_hat,
                        const float* __restrict__ d_pi_hat, const float* __restrict__ d_y_hat,
                        unsigned char* __restrict__ dgimg, float* __restrict__ dl_out, float* __restrict__ dx,
-                       int R, int L, int W) {
+                       const uint32_t* __restrict__ cotmax, int R, int L, int W) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // (offset arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared
     //  address space and emits LDS / STS instead of generic LD / ST)
@@ -95,7 +90,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
     }
     for (int i = tid; i < 64 * 64; i += BT_THREADS) {
         const int n = i >> 6, k = i & 63;
-        *reinterpret_cast<__nv_bfloat16*>(sI + sw128_offset(64, n, k)) = __float2bfloat16_rn(n == k ? 1.0f : 0.0f);
+        *reinterpret_cast<__half*>(sI + sw128_offset(64, n, k)) = __float2half_rn(n == k ? 1.0f : 0.0f);
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -120,7 +115,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
         // ===================== MMA issuer =============================================================
         // The whole warp walks the loop (all lanes wait on the barriers); one elected lane issues (tc.cuh::elect_one).
         {
-            constexpr uint32_t idesc256 = tc_idesc(BT_M, 256, 1), idesc64 = tc_idesc(BT_M, 64, 1);
+            constexpr uint32_t idesc256 = tc_idesc(BT_M, 256, 0), idesc64 = tc_idesc(BT_M, 64, 0);     // fp16 operands
             const uint32_t a_addr = smem_u32(sA), i_addr = smem_u32(sI);
             const uint64_t ad0 = tc_smem_desc(a_addr), idd = tc_smem_desc(i_addr);
             uint32_t it = 0;
@@ -208,6 +203,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
         const size_t gs = (size_t)L * R32 * 32 * LPG_H;
         uint32_t ait = 0;
         const uint32_t sA_u32 = smem_u32(sA);
+        const float S = cotmax ? cot_scale_from_max(*cotmax) : 1.0f;      // power of two: scaling is exact
         // ---- software pipeline: the factor loads of the next 8-unit chunk and the head cotangents of the
         //      next timestep are issued one iteration ahead (across unit-block / timestep boundaries) ----
         struct FacLoads { uint4 r, z, n, hn, hx; };              // gates of step t, h of step t+1 (the carry h')
@@ -260,8 +256,8 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
 #pragma unroll
                 for (int i = 0; i < 8; ++i) s = fmaf(yh[i], dy[i], s);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dl[i] = rv ? yh[i] * (dy[i] - s) : 0.0f;
-                dpi = rv ? rc.dpi : 0.0f;
+                for (int i = 0; i < 8; ++i) dl[i] = rv ? S * (yh[i] * (dy[i] - s)) : 0.0f;
+                dpi = rv ? S * rc.dpi : 0.0f;
                 if (hf == 0 && rv) {
                     float4* qo = reinterpret_cast<float4*>(dl_out + tok * 8);
                     qo[0] = make_float4(dl[0], dl[1], dl[2], dl[3]);
@@ -324,8 +320,8 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                         ghn[e] = gan[e] * gr_[e];
                         gr[e] = ghn[e] * hn_[e] * (1.0f - gr_[e]);
                         gz[e] = dh * (nd_hp * hx[e] - gn_[e]) * zz[e] * omz;
-                        const float cz = dh * zz[e];
-                        czh[e] = __bfloat162float(__float2bfloat16_rn(cz));
+                        const float cz = fminf(fmaxf(dh * zz[e], -65504.0f), 65504.0f);
+                        czh[e] = __half2float(__float2half_rn(cz));
                         czl[e] = cz - czh[e];
                         {
                             const float4 w0 = *reinterpret_cast<const float4*>(sWi + u * 8), w1 = *reinterpret_cast<const float4*>(sWi + u * 8 + 4);
@@ -337,12 +333,12 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                     // (they finished long ago: this chunk's math alone takes longer)
                     if (c8 == 0 && ait > 0) mbar_wait(&a_empty, (ait & 1) ^ 1);
                     const uint32_t so = sA_u32 + sw128_offset(BT_M, rl, hf * 32 + c8 * 8);
-                    st_shared_v4(so + 0 * BT_ACHUNK, pack8bf(gr));
-                    st_shared_v4(so + 1 * BT_ACHUNK, pack8bf(gz));
-                    st_shared_v4(so + 2 * BT_ACHUNK, pack8bf(ghn));
-                    st_shared_v4(so + 3 * BT_ACHUNK, pack8bf(czh));
-                    st_shared_v4(so + 4 * BT_ACHUNK, pack8bf(czl));
-                    st_shared_v4(so + 5 * BT_ACHUNK, pack8bf(gan));
+                    st_shared_v4(so + 0 * BT_ACHUNK, pack8h_sat(gr));
+                    st_shared_v4(so + 1 * BT_ACHUNK, pack8h_sat(gz));
+                    st_shared_v4(so + 2 * BT_ACHUNK, pack8h_sat(ghn));
+                    st_shared_v4(so + 3 * BT_ACHUNK, pack8h_sat(czh));
+                    st_shared_v4(so + 4 * BT_ACHUNK, pack8h_sat(czl));
+                    st_shared_v4(so + 5 * BT_ACHUNK, pack8h_sat(gan));
                     if (c8 & 1) {                                  // K-step 2 hf + (c8 >> 1) of this unit block is complete
                         fence_proxy_async_smem();
                         tc_fence_before();
@@ -370,15 +366,15 @@ static size_t gru_bwd_tc_smem() {
 
 extern "C" int toued_gru_backward_tc(const uint8_t* done, const float* lpg_params, const void* whb_img,
                                      const void* h16, const void* fac, const float* y_hat, const float* d_pi_hat,
-                                     const float* d_y_hat, void* dgimg, float* dl, float* dx, int n_agents,
-                                     int n_workers, int rollout_len, int lifetime_conditioning, void* stream) {
+                                     const float* d_y_hat, void* dgimg, float* dl, float* dx, const uint32_t* cotangent_max,
+                                     int n_agents, int n_workers, int rollout_len, int lifetime_conditioning, void* stream) {
     const int R = n_agents * n_workers;
     TOUED_CHECK(R > 0 && rollout_len > 0, "toued_gru_backward_tc: empty problem");
     const size_t smem = gru_bwd_tc_smem();
     TOUED_CUDA(cudaFuncSetAttribute(gru_backward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gru_backward_tc_kernel<<<(R + BT_M - 1) / BT_M, BT_THREADS, smem, (cudaStream_t)stream>>>(
         done, lpg_params, lifetime_conditioning ? 7 : 5, (const unsigned char*)whb_img, (const __half*)h16,
-        (const __half*)fac, y_hat, d_pi_hat, d_y_hat, (unsigned char*)dgimg, dl, dx, R, rollout_len, n_workers);
+        (const __half*)fac, y_hat, d_pi_hat, d_y_hat, (unsigned char*)dgimg, dl, dx, cotangent_max, R, rollout_len, n_workers);
     TOUED_LAUNCH_CHECK();
     return 0;
 }

@@ -16,7 +16,7 @@
 //     accumulator and commits to mbarriers;
 //   * 8 epilogue warps tcgen05.ld the four gate pre-activations of their (row, 8 units),
 //     apply the flax GRUCell gate math, write h_t (fp16) into A[nxt] and
-//     h (fp16), the five reverse-pass factors (fp16) and the masked carry h' (bf16 tile image) to HBM, and accumulate the two heads
+//     h (fp16), the five reverse-pass factors (fp16) and the masked carry h' (fp16 tile image) to HBM, and accumulate the two heads
 //     (pi_hat, y_hat logits) on relu(h_t) in registers.
 // fp16 operands / fp32 accumulate: the hidden state is quantised to fp16 once per step (|h| < 1).
 // Parity is checked against the exact-fp32 SIMT kernel and the fp64 oracle with a stated tolerance.
@@ -342,14 +342,6 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                     r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
                     return r;
                 };
-                auto pack8b = [](const float (&v)[8]) {
-                    uint4 r;
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
-                    r.x = *reinterpret_cast<uint32_t*>(&h0); r.y = *reinterpret_cast<uint32_t*>(&h1);
-                    r.z = *reinterpret_cast<uint32_t*>(&h2); r.w = *reinterpret_cast<uint32_t*>(&h3);
-                    return r;
-                };
                 const uint4 hpk = pack8(hv);
                 {   // relu(h_t) of this pass -> K = 16 tile (8 TMEM columns) for the heads MMA
                     const uint32_t sb = it & 3;
@@ -379,10 +371,11 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                         *reinterpret_cast<uint4*>(fac + 3 * gs + so) = pack8(hn);
                     }
                     if (hpimg) {
-                        // h' consumed at step t-1 (= masked h_t), bf16 token-tile image for the weight-gradient GEMM
+                        // h' consumed at step t-1 (= masked h_t): fp16 token-tile image for the weight-gradient GEMM (the very fp16
+                        // values the recurrence used: no second rounding)
                         if (t > 0)
                             *reinterpret_cast<uint4*>(hpimg + tile_img_offset((size_t)(t - 1) * Rp + row, 4, u0)) =
-                                zero_next ? make_uint4(0u, 0u, 0u, 0u) : pack8b(hv);
+                                zero_next ? make_uint4(0u, 0u, 0u, 0u) : hpk;
                         if (t == L - 1)
                             *reinterpret_cast<uint4*>(hpimg + tile_img_offset((size_t)t * Rp + row, 4, u0)) = make_uint4(0u, 0u, 0u, 0u);
                     }

@@ -14,6 +14,7 @@
 //   toued_reduce_partials  grad[p] (+)= sum_s partial[s][p]
 //   toued_adam           optax.scale_by_adam -> scale(lr) -> scale(-1)  (models/optim.py:12-17, Q9)
 #include "lpg_common.cuh"
+#include "tc.cuh"
 #include "../../include/toued.h"
 
 __device__ __forceinline__ void cp_async16z(void* smem, const void* gmem, bool valid) {
@@ -358,8 +359,8 @@ constexpr int EM_SREC = 44;            // y[8] | da[16] | relu(a) dp [16] | dp |
 __global__ void __launch_bounds__(256, 2)
 embed_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ done,
                       const float* __restrict__ critic, const float* __restrict__ lpg, int emb_off,
-                      const float* __restrict__ dx, float* __restrict__ partial, int n_agents, int W, int L, int D,
-                      int accumulate) {
+                      const float* __restrict__ dx, float* __restrict__ partial, const uint32_t* __restrict__ cotmax,
+                      int n_agents, int W, int L, int D, int accumulate) {
     // phase 1: each thread back-propagates its token through the two embedding-MLP applications (one pass over the
     //          weights for both) and leaves (y[8], da[16], relu(a)*dp [16], dp) per application in shared memory;
     // phase 2: the block's 2 x 256 samples are split over 4 pairs of warps; in a pair, 32 threads own a 1 x 4 block of
@@ -368,6 +369,8 @@ embed_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
     //          fixed order at the end (deterministic).
     __shared__ float sp[EM_TOTAL];
     __shared__ float part[4][EM_TOTAL + 3];
+    // dx of the tensor-core BPTT kernel is in units of the launch's cotangent scale S (tc.cuh)
+    const float inv_s = cotmax ? 1.0f / cot_scale_from_max(*cotmax) : 1.0f;
     extern __shared__ __align__(16) float srec[];          // [2 * 256][44] = 88 KB (dynamic)
     const int tid = threadIdx.x;
     for (int i = tid; i < EM_TOTAL; i += 256) sp[i] = lpg[emb_off + i];
@@ -400,8 +403,8 @@ embed_backward_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict
             tab_logits8<8>(ct, D, obs[((size_t)n * (L + 1) + t + 1) * W + w], zy);
             softmax_c<8>(zy, y[1]);
             const float2 d = *reinterpret_cast<const float2*>(dx + ((size_t)t * R + (size_t)n * W + w) * 2);
-            dp[0] = d.x;
-            dp[1] = done[g] ? 0.0f : d.y;
+            dp[0] = d.x * inv_s;
+            dp[1] = done[g] ? 0.0f : d.y * inv_s;
         }
         float* r0 = srec + (size_t)tid * EM_SREC;
         float* r1 = srec + (size_t)(256 + tid) * EM_SREC;
@@ -497,7 +500,7 @@ extern "C" int toued_lpg_wgrad(const int32_t* obs, const uint8_t* done, const fl
     }
     TOUED_CUDA(cudaFuncSetAttribute(embed_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EM_SMEM));
     embed_backward_kernel<<<EM_SPLITS, 256, EM_SMEM, st>>>(obs, done, critic, lpg_params, lpg_offsets(lifetime_conditioning ? 7 : 5).e_w0,
-                                                      dx, p_em, n_agents, n_workers, L, obs_dim, accumulate);
+                                                      dx, p_em, nullptr, n_agents, n_workers, L, obs_dim, accumulate);
     TOUED_LAUNCH_CHECK();
     return 0;
 }
@@ -549,13 +552,14 @@ extern "C" int toued_lpg_wgrad_workspace_offset(int which) {
 
 // embedding-MLP gradients only (shared by the fp32 and the tensor-core reverse pass)
 extern "C" int toued_lpg_wgrad_embed(const int32_t* obs, const uint8_t* done, const float* critic, const float* lpg_params,
-                                     const float* dx, float* workspace, int n_agents, int n_workers, int rollout_len,
-                                     int obs_dim, int lifetime_conditioning, int accumulate, void* stream) {
+                                     const float* dx, float* workspace, const uint32_t* cotangent_max, int n_agents,
+                                     int n_workers, int rollout_len, int obs_dim, int lifetime_conditioning, int accumulate,
+                                     void* stream) {
     float* p_em = workspace + toued_lpg_wgrad_workspace_offset(2);
     TOUED_CUDA(cudaFuncSetAttribute(embed_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EM_SMEM));
     embed_backward_kernel<<<EM_SPLITS, 256, EM_SMEM, (cudaStream_t)stream>>>(
-        obs, done, critic, lpg_params, lpg_offsets(lifetime_conditioning ? 7 : 5).e_w0, dx, p_em, n_agents, n_workers,
-        rollout_len, obs_dim, accumulate);
+        obs, done, critic, lpg_params, lpg_offsets(lifetime_conditioning ? 7 : 5).e_w0, dx, p_em, cotangent_max, n_agents,
+        n_workers, rollout_len, obs_dim, accumulate);
     TOUED_LAUNCH_CHECK();
     return 0;
 }
@@ -618,6 +622,36 @@ extern "C" int toued_adam_dev(float* params, const float* grad, float* mu, float
     adam_dev_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params, grad, mu, nu, count_dev, n, lr, b1, b2, eps);
     TOUED_LAUNCH_CHECK();
     count_incr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(count_dev);
+    TOUED_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// max |cotangent| of one reverse-pass launch (d pi_hat f32[n_tok], d y_hat f32[n_tok][8]) as the bit pattern of a
+// non-negative float (integer order == float order, so atomicMax is exact and order-independent): the tensor-core
+// reverse kernels derive their power-of-two operand scale from it (tc.cuh::cot_scale_from_max).
+__global__ void cot_max_kernel(const float* __restrict__ d_pi_hat, const float* __restrict__ d_y_hat, size_t n_tok,
+                               uint32_t* __restrict__ out_bits) {
+    float m = 0.f;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_tok; i += stride) m = fmaxf(m, fabsf(d_pi_hat[i]));
+    const float4* y4 = reinterpret_cast<const float4*>(d_y_hat);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_tok; i += stride) {
+        const float4 v = y4[i];
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
+}
+
+extern "C" int toued_cotangent_max(const float* d_pi_hat, const float* d_y_hat, int n_agents, int n_workers, int rollout_len,
+                                   uint32_t* out_bits, void* stream) {
+    const size_t n_tok = (size_t)n_agents * n_workers * rollout_len;
+    TOUED_CHECK(n_tok > 0 && out_bits != nullptr, "toued_cotangent_max: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    TOUED_CUDA(cudaMemsetAsync(out_bits, 0, sizeof(uint32_t), st));
+    cot_max_kernel<<<296, 256, 0, st>>>(d_pi_hat, d_y_hat, n_tok, out_bits);
     TOUED_LAUNCH_CHECK();
     return 0;
 }

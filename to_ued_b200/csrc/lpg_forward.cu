@@ -193,10 +193,10 @@ lpg_prepare_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__ 
     xo[0] = make_float4(reward[g], d, pa + 1e-8f, pyt);             // lpg_agent.py:41-43 (pi + 1e-8)
     const float4 v1 = make_float4(pyt1, cond ? (float)step[n] : 0.0f, cond ? (float)levels[n].lifetime : 0.0f, 1.0f);
     xo[1] = v1;
-    if (ximg) {      // bf16 token-tile image (one 64-column group, columns 8..63 stay zero) for the weight-gradient GEMM
+    if (ximg) {      // fp16 token-tile image (one 64-column group, columns 8..63 stay zero) for the weight-gradient GEMM
         const size_t Rp = ((size_t)n_agents * W + 63) & ~(size_t)63;
-        __nv_bfloat162 b0 = __floats2bfloat162_rn(reward[g], d), b1 = __floats2bfloat162_rn(pa + 1e-8f, pyt);
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(v1.x, v1.y), b3 = __floats2bfloat162_rn(v1.z, v1.w);
+        __half2 b0 = __floats2half2_rn(reward[g], d), b1 = __floats2half2_rn(pa + 1e-8f, pyt);
+        __half2 b2 = __floats2half2_rn(v1.x, v1.y), b3 = __floats2half2_rn(v1.z, v1.w);
         uint4 pk;
         pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
         pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);

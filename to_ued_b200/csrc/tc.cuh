@@ -148,3 +148,26 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+
+// ---- scaled fp16 operands of the tensor-core reverse pass -----------------------------------------------------------
+// The reverse pass is linear in the cotangents (d pi_hat, d y_hat), which are tiny (pre-scaled by 1 / N_global): far
+// below fp16's range but fine for bf16 -- at 8 instead of 11 significant bits.  The tensor-core reverse kernels therefore
+// run on cotangents multiplied by a power of two S chosen per launch from max |cotangent| (toued_cotangent_max), use fp16
+// operands everywhere (dG, z * dh, Wh, h', x: 8x finer than bf16; h' is even exact, it IS fp16), convert with saturation,
+// and multiply their fp32 results by 1 / S when they leave the kernel.  S puts the largest cotangent at [2^3, 2^4): a
+// factor 2^12 of headroom for growth along the 20-step chain before saturation, ~2^-27 of the maximum before underflow.
+__device__ __forceinline__ float cot_scale_from_max(uint32_t max_bits) {
+    if (max_bits == 0u || max_bits >= 0x7F800000u) return 1.0f;           // no signal, or inf / nan: leave unscaled
+    const int e = (int)(max_bits >> 23) - 127;                            // floor(log2(max))
+    const int s = min(max(3 - e, -100), 100);
+    return __uint_as_float((uint32_t)(s + 127) << 23);                     // 2^s
+}
+// two fp32 -> packed fp16x2 with saturation to +-65504 (lo in the low half)
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint4 pack8h_sat(const float (&v)[8]) {
+    return make_uint4(pack_h2_sat(v[0], v[1]), pack_h2_sat(v[2], v[3]), pack_h2_sat(v[4], v[5]), pack_h2_sat(v[6], v[7]));
+}

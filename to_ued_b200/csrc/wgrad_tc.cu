@@ -2,7 +2,7 @@
 // (the parameter-gradient sum of jax.grad through models/lpg.py:29, flax GRUCell hr/hz/hn kernels).
 //
 // Both operands are contracted over tokens, i.e. they are MN-major for tcgen05: the 64-token x 64-column
-// sub-tiles of the bf16 token tile images written by the forward (h') and backward (dG) kernels are
+// sub-tiles of the fp16 token tile images written by the forward (h') and backward (S * dG, tc.cuh) kernels are
 // bulk-copied (cp.async.bulk) into shared memory and used as-is.  A CTA owns one 128 (j) x 384 (c)
 // output tile (fp32 accumulators in 384 TMEM columns) and a contiguous range of token blocks; the four
 // tile types of one token range are adjacent CTAs so they share their operand stream through L2.
@@ -21,7 +21,7 @@ constexpr int WT_STAGE = 9 * 8192;         // dWh tiles: 2 A + 6 B sub-tiles of 
 __global__ void __launch_bounds__(WT_THREADS, 1)
 wgrad_wh_tc_kernel(const unsigned char* __restrict__ hpimg, const unsigned char* __restrict__ dgimg,
                    const unsigned char* __restrict__ ximg, float* __restrict__ partial, float* __restrict__ small_partial,
-                   int n_tok_blocks, int blocks_per_split, int accumulate) {
+                   const uint32_t* __restrict__ cotmax, int n_tok_blocks, int blocks_per_split, int accumulate) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // (offset arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared
     //  address space and emits LDS / STS instead of generic LD / ST)
@@ -69,7 +69,7 @@ wgrad_wh_tc_kernel(const unsigned char* __restrict__ hpimg, const unsigned char*
         }
     } else if (warp == 5) {
         {   // all lanes wait, one elected lane issues (tc.cuh::elect_one)
-            constexpr uint32_t idesc = tc_idesc_mn(128, 192, 1), idesc_x = tc_idesc_mn(64, 256, 1);   // x tiles: M = 64 (one group, 8 rows used)
+            constexpr uint32_t idesc = tc_idesc_mn(128, 192, 0), idesc_x = tc_idesc_mn(64, 256, 0);   // fp16; x tiles: M = 64 (one group, 8 rows used)
             for (int i = 0; i < nblk; ++i) {
                 const int s = i % WT_NS;
                 mbar_wait(&full[s], (i / WT_NS) & 1);
@@ -105,6 +105,8 @@ wgrad_wh_tc_kernel(const unsigned char* __restrict__ hpimg, const unsigned char*
         // epilogue: TMEM lane = j within the tile
         mbar_wait(&done_bar, 0);
         tc_fence_after();
+        // the dG image is in units of the launch's cotangent scale S (tc.cuh): take it back out of the fp32 sums
+        const float inv_s = cotmax ? 1.0f / cot_scale_from_max(*cotmax) : 1.0f;
         if (xt) {
             // rows 0..7 of the x tile: dWi (rows q < X), dbi (row 7) and dbhn (row 7 of the dhn columns).
             // Always accumulates: the head-gradient kernel has initialised this split's small-partial area.
@@ -134,7 +136,7 @@ wgrad_wh_tc_kernel(const unsigned char* __restrict__ hpimg, const unsigned char*
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) { const int d = dst_of(c + 8 * i + e); if (d >= 0) out[d] = o[i][e] + v[i][e]; }
+                            for (int e = 0; e < 8; ++e) { const int d = dst_of(c + 8 * i + e); if (d >= 0) out[d] = fmaf(v[i][e], inv_s, o[i][e]); }
                     }
                 }
             }
@@ -163,8 +165,8 @@ wgrad_wh_tc_kernel(const unsigned char* __restrict__ hpimg, const unsigned char*
 #pragma unroll
                     for (int e = 0; e < 8; ++e) v[e] = 0.f;
                 }
-                p[2 * i] = make_float4(v[0] + pre[2 * i].x, v[1] + pre[2 * i].y, v[2] + pre[2 * i].z, v[3] + pre[2 * i].w);
-                p[2 * i + 1] = make_float4(v[4] + pre[2 * i + 1].x, v[5] + pre[2 * i + 1].y, v[6] + pre[2 * i + 1].z, v[7] + pre[2 * i + 1].w);
+                p[2 * i] = make_float4(fmaf(v[0], inv_s, pre[2 * i].x), fmaf(v[1], inv_s, pre[2 * i].y), fmaf(v[2], inv_s, pre[2 * i].z), fmaf(v[3], inv_s, pre[2 * i].w));
+                p[2 * i + 1] = make_float4(fmaf(v[4], inv_s, pre[2 * i + 1].x), fmaf(v[5], inv_s, pre[2 * i + 1].y), fmaf(v[6], inv_s, pre[2 * i + 1].z), fmaf(v[7], inv_s, pre[2 * i + 1].w));
             }
         }
         }
@@ -192,7 +194,9 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
 }
 __global__ void __launch_bounds__(256)
 wgrad_heads_stream_kernel(const __half* __restrict__ h16, const float* __restrict__ d_pi_hat, const float* __restrict__ dl,
-                          float* __restrict__ partial, int R, int L, int blocks_per_split, int accumulate) {
+                          float* __restrict__ partial, const uint32_t* __restrict__ cotmax, int R, int L, int blocks_per_split,
+                          int accumulate) {
+    const float inv_s = cotmax ? 1.0f / cot_scale_from_max(*cotmax) : 1.0f;      // dl arrives in units of S, d_pi_hat does not
     extern __shared__ __align__(128) unsigned char hsm[];     // [HT_DEPTH][256 threads][HT_SLOT]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = blockIdx.x * 8 + warp;            // 0..31
@@ -241,7 +245,8 @@ wgrad_heads_stream_kernel(const __half* __restrict__ h16, const float* __restric
         if (row >= R) continue;
         const uint4 raw = *reinterpret_cast<const uint4*>(st);
         const float4 d0 = *reinterpret_cast<const float4*>(st + 16), d1 = *reinterpret_cast<const float4*>(st + 32);
-        const float dv[9] = {*reinterpret_cast<const float*>(st + 48), d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        const float dv[9] = {*reinterpret_cast<const float*>(st + 48), d0.x * inv_s, d0.y * inv_s, d0.z * inv_s, d0.w * inv_s,
+                             d1.x * inv_s, d1.y * inv_s, d1.z * inv_s, d1.w * inv_s};
         const __half2* hh = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
@@ -285,16 +290,17 @@ wgrad_heads_stream_kernel(const __half* __restrict__ h16, const float* __restric
 // ---- head gradients on the tensor cores (R % 32 == 0) ---------------------------------------------------
 // dw_pi / dW_y = relu(h)^T [256 units x tokens] . [d pi_hat | dl] [tokens x 9]: a GEMM contracted over tokens.
 // A 32-row block of the RB32 activation layout (16 KB contiguous) is, as it lies in memory, an MN-major
-// no-swizzle tcgen05 operand (k = rows).  Per block: TMA bulk copy -> four warps apply relu and convert
-// fp16 -> bf16 in place and build the B operand from the fp32 cotangents as a bf16 hi + lo pair (N = 32:
-// columns 0..15 hi, 16..31 lo, so the cotangents keep ~16 mantissa bits) -> 4 MMAs (M128 N32 K16).
+// no-swizzle tcgen05 operand (k = rows).  Per block: TMA bulk copy -> four warps apply relu in place (fp16) and
+// build the B operand from the fp32 cotangents, scaled by the launch's S (tc.cuh), as an fp16 hi + lo pair (N = 32:
+// columns 0..15 hi, 16..31 lo, so the cotangents keep ~22 mantissa bits) -> 4 MMAs (M128 N32 K16).
 constexpr int HM_NS = 4;
 constexpr int HM_A = 16384, HM_RAW = 1024 + 128, HM_B = 2048;
 constexpr int HM_STAGE = HM_A + HM_RAW + HM_B;            // 19584 B (multiple of 128)
 constexpr int HM_THREADS = 192;
 __global__ void __launch_bounds__(HM_THREADS, 1)
 wgrad_heads_mma_kernel(const __half* __restrict__ h16, const float* __restrict__ d_pi_hat, const float* __restrict__ dl,
-                       float* __restrict__ partial, int R, int L, int blocks_per_split, int accumulate) {
+                       float* __restrict__ partial, const uint32_t* __restrict__ cotmax, int R, int L, int blocks_per_split,
+                       int accumulate) {
     extern __shared__ __align__(1024) unsigned char hm_raw[];
     unsigned char* smem = hm_raw + ((128u - (smem_u32(hm_raw) & 127u)) & 127u);
     __shared__ __align__(8) uint64_t full[HM_NS], ready[HM_NS], empty[HM_NS], done_bar;
@@ -333,9 +339,8 @@ wgrad_heads_mma_kernel(const __half* __restrict__ h16, const float* __restrict__
         }
     } else if (warp == 5) {
         {
-            // (kind::f16 needs A and B in the same 16-bit format on this part: fp16 x bf16 traps, so relu(h) is
-            //  converted to bf16 by the transform warps)
-            constexpr uint32_t idesc = tc_idesc_mn(128, 32, 1);
+            // (kind::f16 needs A and B in the same 16-bit format on this part: fp16 x bf16 traps; both are fp16 here)
+            constexpr uint32_t idesc = tc_idesc_mn(128, 32, 0);
             for (int i = 0; i < nblk; ++i) {
                 const int s = i % HM_NS;
                 mbar_wait(&ready[s], (i / HM_NS) & 1);
@@ -362,39 +367,36 @@ wgrad_heads_mma_kernel(const __half* __restrict__ h16, const float* __restrict__
         float hb[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) hb[i] = 0.f;
+        const float S = cotmax ? cot_scale_from_max(*cotmax) : 1.0f, inv_s = 1.0f / S;
         for (int i = 0; i < nblk; ++i) {
             const int s = i % HM_NS;
             mbar_wait(&full[s], (i / HM_NS) & 1);
             unsigned char* st = smem + s * HM_STAGE;
-            // relu + fp16 -> bf16 in place: 1024 16-byte groups, 8 per thread (consecutive threads, consecutive groups)
+            // relu in place (fp16): 1024 16-byte groups, 8 per thread (consecutive threads, consecutive groups)
+            const __half2 z2 = __float2half2_rn(0.0f);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 uint4* pp = reinterpret_cast<uint4*>(st) + q * 128 + tid;
-                const uint4 raw = *pp;
-                const __half2* hh = reinterpret_cast<const __half2*>(&raw);
-                uint4 o;
-                uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+                uint4 raw = *pp;
+                __half2* hh = reinterpret_cast<__half2*>(&raw);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 f = __half22float2(hh[e]);
-                    const __nv_bfloat162 b = __floats2bfloat162_rn(fmaxf(f.x, 0.0f), fmaxf(f.y, 0.0f));
-                    ow[e] = *reinterpret_cast<const uint32_t*>(&b);
-                }
-                *pp = o;
+                for (int e = 0; e < 4; ++e) hh[e] = __hmax2(hh[e], z2);
+                *pp = raw;
             }
             if (warp == 0) {
                 // B operand for row `lane`: [n-group g][k = row][8] bf16; groups 0,1 = hi of (d pi_hat, dl[0..7], 0..),
                 // groups 2,3 = lo
                 const float4 d0 = *reinterpret_cast<const float4*>(st + HM_A + lane * 32), d1 = *reinterpret_cast<const float4*>(st + HM_A + lane * 32 + 16);
-                const float dv[9] = {*reinterpret_cast<const float*>(st + HM_A + 1024 + lane * 4), d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                // in units of S: d_pi_hat is scaled here, dl was written scaled by the BPTT kernel
+                const float dv[9] = {S * *reinterpret_cast<const float*>(st + HM_A + 1024 + lane * 4), d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
                 float hi[9], lo[9];
 #pragma unroll
                 for (int j = 0; j < 9; ++j) {
-                    hi[j] = __bfloat162float(__float2bfloat16_rn(dv[j]));
+                    hi[j] = __half2float(__float2half_rn(fminf(fmaxf(dv[j], -65504.0f), 65504.0f)));
                     lo[j] = dv[j] - hi[j];
                     hb[j] += dv[j];
                 }
-                auto pk = [](float a, float b) { const __nv_bfloat162 v = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&v); };
+                auto pk = [](float a, float b) { return pack_h2_sat(a, b); };
                 unsigned char* bp = st + HM_A + HM_RAW + lane * 16;
                 *reinterpret_cast<uint4*>(bp) = make_uint4(pk(hi[0], hi[1]), pk(hi[2], hi[3]), pk(hi[4], hi[5]), pk(hi[6], hi[7]));
                 *reinterpret_cast<uint4*>(bp + 512) = make_uint4(pk(hi[8], 0.f), 0u, 0u, 0u);
@@ -437,9 +439,9 @@ wgrad_heads_mma_kernel(const __half* __restrict__ h16, const float* __restrict__
 #pragma unroll
                 for (int j = 0; j < 8; ++j) prev[1 + j] = wy[j];
             }
-            out[SMT_WPI + u] = prev[0] + g[0];
+            out[SMT_WPI + u] = fmaf(g[0], inv_s, prev[0]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) wy[j] = prev[1 + j] + g[1 + j];
+            for (int j = 0; j < 8; ++j) wy[j] = fmaf(g[1 + j], inv_s, prev[1 + j]);
         }
         if (warp == 0) {
 #pragma unroll
@@ -447,6 +449,7 @@ wgrad_heads_mma_kernel(const __half* __restrict__ h16, const float* __restrict__
                 float v = hb[i];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                v *= inv_s;
                 if (lane == i) out[SMT_BPI + i] = accumulate ? out[SMT_BPI + i] + v : v;
             }
         }
@@ -467,7 +470,8 @@ extern "C" int toued_wgrad_tc_small_splits(void) { return HT_SPLITS; }
 
 extern "C" int toued_lpg_wgrad_tc(const void* hpimg, const void* dgimg, const void* ximg, const void* h16,
                                   const float* d_pi_hat, const float* dl, float* wh_partials, float* small_partials,
-                                  int n_agents, int n_workers, int rollout_len, int accumulate, void* stream) {
+                                  const uint32_t* cotangent_max, int n_agents, int n_workers, int rollout_len, int accumulate,
+                                  void* stream) {
     const int R = n_agents * n_workers, L = rollout_len;
     TOUED_CHECK(R > 0 && L > 0, "toued_lpg_wgrad_tc: empty problem");
     cudaStream_t st = (cudaStream_t)stream;
@@ -481,19 +485,19 @@ extern "C" int toued_lpg_wgrad_tc(const void* hpimg, const void* dgimg, const vo
         constexpr int msmem = HM_NS * HM_STAGE + 128;
         TOUED_CUDA(cudaFuncSetAttribute(wgrad_heads_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
         wgrad_heads_mma_kernel<<<HT_SPLITS, HM_THREADS, msmem, st>>>((const __half*)h16, d_pi_hat, dl, small_partials,
-                                                                    R, L, rbps, accumulate);
+                                                                    cotangent_max, R, L, rbps, accumulate);
     } else {
         constexpr int hsmem = HT_DEPTH * 256 * HT_SLOT;
         TOUED_CUDA(cudaFuncSetAttribute(wgrad_heads_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hsmem));
         wgrad_heads_stream_kernel<<<dim3(4, HT_SPLITS), 256, hsmem, st>>>((const __half*)h16, d_pi_hat, dl, small_partials,
-                                                                         R, L, rbps, accumulate);
+                                                                         cotangent_max, R, L, rbps, accumulate);
     }
     TOUED_LAUNCH_CHECK();
     const size_t smem = WT_NS * WT_STAGE + 1024;
     TOUED_CUDA(cudaFuncSetAttribute(wgrad_wh_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wgrad_wh_tc_kernel<<<6 * WT_SPLITS, WT_THREADS, smem, st>>>((const unsigned char*)hpimg, (const unsigned char*)dgimg,
                                                                 (const unsigned char*)ximg, wh_partials, small_partials,
-                                                                n_tb, bps, accumulate);
+                                                                cotangent_max, n_tb, bps, accumulate);
     TOUED_LAUNCH_CHECK();
     return 0;
 }

@@ -68,8 +68,10 @@ class MetaGradWorkspace:
         self.ab_scratch = torch.empty(_lib.lib().toued_agent_scratch_floats(N, W, L, obs_dim), dtype=f32, device=device)
         if self.tape.precision == "tc":
             Rp = (R + 63) // 64 * 64
-            self.whb_img = torch.empty(256 * 768, dtype=torch.bfloat16, device=device)
-            # bf16 token-tile image of (dar, daz, dhn, dan): 16 column groups of 64
+            self.whb_img = torch.empty(256 * 768, dtype=torch.float16, device=device)
+            # max |cotangent| of every update's reverse launch (scaled fp16 operands, csrc/tc.cuh)
+            self.cotmax = torch.zeros(K, dtype=torch.int32, device=device)
+            # fp16 token-tile image of S * (dar, daz, dhn, dan): 16 column groups of 64
             # (double-buffered over the update index like the cotangents: the weight-gradient GEMMs of update k run on
             #  their own stream next to the BPTT of update k-1)
             self.dgimg2 = [torch.zeros(L * Rp * 1024 * 2, dtype=torch.uint8, device=device) for _ in range(2)]
@@ -318,6 +320,8 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
             if k + 2 <= K - 1:
                 st.wait_event(ev["wg"][k + 2])              # the cotangent buffer is free again
             _agent_backward(ws, tape, k, buf, _lib.stream_ptr())
+            _lib.call("toued_cotangent_max", p(ws.d_pi_hat2[buf]), p(ws.d_y_hat2[buf]), nb, W, L, p(ws.cotmax[k:k + 1]),
+                      _lib.stream_ptr())
             ev["ab"][k].record(st)
         with torch.cuda.stream(streams[slot]):
             st = streams[slot]
@@ -328,7 +332,7 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
                 st.wait_event(ev["wg"][k + 2])              # ... and so have the dG image and dl [k & 1]
             _lib.call("toued_gru_backward_tc", p(tape.done[k]), p(lpg), p(ws.whb_img), p(tape.h16[k]),
                       p(tape.fac[k]), p(tape.y_hat[k]), p(ws.d_pi_hat2[buf]), p(ws.d_y_hat2[buf]), p(ws.dgimg2[buf]), p(ws.dl2[buf]),
-                      p(ws.dx2[buf]), nb, W, L, cond, s)
+                      p(ws.dx2[buf]), p(ws.cotmax[k:k + 1]), nb, W, L, cond, s)
             ev["bwd"][k].record(st)
             _phase(f"bwd{k}", mb, st)
         with torch.cuda.stream(wg_streams[slot]):
@@ -336,14 +340,15 @@ def lpg_meta_grad_train_step(rng, lpg_train_state: LPGTrainState, agent_states: 
             st.wait_event(ev["bwd"][k])
             _lib.call("toued_lpg_wgrad_tc", p(tape.hpimg[k]), p(ws.dgimg2[buf]), p(tape.ximg[k]), p(tape.h16[k]),
                       p(ws.d_pi_hat2[buf]), p(ws.dl2[buf]), p(ws.partials), p(ws.partials[ws.off_small:]),
-                      nb, W, L, 0 if first else 1, _lib.stream_ptr())
+                      p(ws.cotmax[k:k + 1]), nb, W, L, 0 if first else 1, _lib.stream_ptr())
             ev["wg"][k].record(st)
             _phase(f"wgrad{k}", mb, st)
         with torch.cuda.stream(em_streams[slot]):
             st = em_streams[slot]
             st.wait_event(ev["bwd"][k])
             _lib.call("toued_lpg_wgrad_embed", p(tape.obs[k]), p(tape.done[k]), p(tape.critic[k]), p(lpg),
-                      p(ws.dx2[buf]), p(ws.partials), nb, W, L, D, cond, 0 if first else 1, _lib.stream_ptr())
+                      p(ws.dx2[buf]), p(ws.partials), p(ws.cotmax[k:k + 1]), nb, W, L, D, cond, 0 if first else 1,
+                      _lib.stream_ptr())
             ev["em"][k].record(st)
 
     def backward_end(mb):

@@ -71,7 +71,7 @@ def _shard(agents, vcs, rank, n_local):
                          critic_state=c.replace(params=c.params[sl].contiguous(), step=c.step[sl].contiguous()),
                          level=level, env_obs=agents.env_obs[sl].contiguous(),
                          env_state=EnvState(agents.env_state.packed[sl].contiguous(), agents.env_state.max_n_objs),
-                         host_step=agents.host_step[sl])
+                         host_step=None if agents.host_step is None else agents.host_step[sl])
     if vcs is not None:
         vcs = vcs.replace(params=vcs.params[sl].contiguous(), step=vcs.step[sl].contiguous())
     return out, vcs
