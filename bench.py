@@ -143,7 +143,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         import statistics
@@ -421,7 +421,8 @@ def run_ours(a):
     # ---- the other scaling mode, measured in the same run (N > 1, default config) ----
     other = None
     if world > 1 and a.config == DEFAULT_CONFIG and not a.no_other_scaling:
-        del wl.step_fn
+        if hasattr(wl.step_fn, "release"):
+            wl.step_fn.release()
         from to_ued_b200.meta.train import _WS_CACHE
         _WS_CACHE.clear()
         torch.cuda.empty_cache()
@@ -434,9 +435,11 @@ def run_ours(a):
                  "agents_per_gpu": n_other // world, "ms_per_step": oms / a.steps, "value": osteps / (oms * 1e-3),
                  "unit": "env-steps/s", "meta_steps_per_s": 1e3 / (oms / a.steps)}
 
+    def _shutdown():
+        from to_ued_b200.util import dist as udist
+        udist.shutdown(*[w.step_fn for w in (wl,) if hasattr(w, "step_fn")], *([wo.step_fn] if other else []))
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _shutdown()
         return
     ms_per_step = dev_ms / a.steps
     value = env_steps / (dev_ms * 1e-3)
@@ -540,8 +543,7 @@ def run_ours(a):
     if other:
         line[other["scaling"] + "_scaling"] = other
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _shutdown()
 
 
 # algorithmic HBM bytes per token of the tensor-core kernels (fp16 gate planes + h, bf16 dG / h' images)

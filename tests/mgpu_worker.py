@@ -15,6 +15,8 @@ N_AGENTS = 8
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("TOUED_WORKER_TIMEOUT", "240")), exit=True)   # a hung rank prints its stack
     mode, out = sys.argv[1], sys.argv[2]
     import train as train_mod
     from to_ued_b200.util import prng, dist as udist
@@ -67,10 +69,7 @@ def main():
     torch.cuda.synchronize()
     if rank == 0:
         torch.save({"hist": hist, "lpg": params.cpu().numpy(), "world": world}, out)
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+    udist.shutdown(step_fn)
 
 
 if __name__ == "__main__":

@@ -112,6 +112,15 @@ class GraphedMetaGradStep:
         self.mvec = metrics["_mvec"]
         self.grad = metrics.get("_grad")
 
+    def release(self):
+        """Drop the captured graph (and its NCCL nodes).  Call before torch.distributed.destroy_process_group():
+        tearing the communicator down while a captured graph still references it blocks."""
+        self.graph = None
+        self.sig = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+
     # ------------------------------------------------------------------------------------------------------------
     def __call__(self, rng, lpg_train_state, agent_states, value_critic_states, **kw):
         ts, ag, vc = lpg_train_state, agent_states, value_critic_states

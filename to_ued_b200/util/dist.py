@@ -77,3 +77,29 @@ def all_reduce_sum(t: torch.Tensor) -> torch.Tensor:
     if d is not None and d.get_world_size() > 1:
         d.all_reduce(t)
     return t
+
+
+def shutdown(*graphed_steps, grace_s: float = 30.0):
+    """Orderly end of a multi-rank run: release captured CUDA graphs (they hold NCCL nodes; destroying the process group
+    underneath them blocks), then destroy the process group.  A watchdog ends the process if the teardown still does
+    not return within ``grace_s`` seconds -- all results have been written by then."""
+    d = _dist()
+    for g in graphed_steps:
+        if hasattr(g, "release"):
+            g.release()
+    if d is None:
+        return
+    import os
+    import sys
+    import threading
+    torch.cuda.synchronize()
+    d.barrier()
+
+    def _bail():
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
+    t = threading.Timer(grace_s, _bail)
+    t.daemon = True
+    t.start()
+    d.destroy_process_group()
+    t.cancel()

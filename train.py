@@ -53,9 +53,13 @@ def make_train(args, rank=0, world=1):
             level_buffer, agent_states, value_critic_states = level_sampler.sample(
                 _rng, level_buffer, agent_states, value_critic_states)
             history.append(metrics)
+        _GRAPHED.append(lpg_train_step_fn)
         return history, train_state, level_buffer
 
     return _train_fn
+
+
+_GRAPHED = []      # step functions created by make_train (released before the process group is torn down)
 
 
 def _shard(agents, vcs, rank, n_local):
@@ -95,6 +99,9 @@ def run_training_experiment(args):
         if args.log:                                 # train.py:68-69
             from to_ued_b200.experiments.logging import log_results
             print("[to_ued_b200] checkpoints:", log_results(args, metrics, train_state, level_buffer))
+    if world > 1:
+        from to_ued_b200.util import dist as udist
+        udist.shutdown(*_GRAPHED)
     return metrics, train_state, level_buffer
 
 
