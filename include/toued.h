@@ -207,6 +207,15 @@ int toued_es_adam(const float* grad_sum, float* mean, float* m, float* v, int po
                   float sigma, float lrate, float beta1, float beta2, float eps, int gen_counter, float mean_decay,
                   void* stream);
 
+/* ---- device level generator (environments/gridworld/configs.py:12-57, environments.py:23-38) -------- */
+/* One LevelRec per key: keys u32[n][2] are the per-level keys the reference passes to reset_env_params
+ * (split(rng, n)); gen_desc is the mode description built by the host (to_ued_b200/environments/gridworld/levelgen.py,
+ * toued_generate_levels_desc_bytes() bytes); buffer_ids i32[n] or NULL (0); lifetimes_out i32[n] or NULL.
+ * Bit-exact with oracle/configs.py under the RNG / float contract of DESIGN.md section 2.            */
+int toued_generate_levels_desc_bytes(void);
+int toued_generate_levels(const void* gen_desc, const uint32_t* keys, const int32_t* buffer_ids, void* levels_out,
+                          int32_t* lifetimes_out, int n_levels, void* stream);
+
 /* ---- double-oracle Nash solver (environments/nash_sampler.py:24-58, util/projection.py:9-38) ------ */
 /* game f32[n][n] (row player x minimises x^T G y), supports = first x_nz / y_nz coordinates, n <= 1024.
  * Averaged iterates of num_iters projected-gradient steps (reference: 10,000 steps, lr 0.01).        */

@@ -28,8 +28,13 @@ def uniform_first_pos(key, n, minval, maxval):
 
 
 def log_uniform(key, shape, minval, maxval):
+    """configs.py:117-126 ``exp(uniform(log lo, log hi))``.  Float contract: the exponential is
+    ``exp_portable`` (individually rounded f32 operations, the same routine as the policy softmax), so that the host
+    numpy generator and the device level generator (csrc/levelgen.cu) produce the same bits; jax's own exp rounding is
+    unknowable here."""
+    from .rollout import exp_portable
     lo, hi = F32(np.log(F32(minval))), F32(np.log(F32(maxval)))
-    return np.exp(prng.uniform(key, shape, lo, hi)).astype(F32)
+    return exp_portable(prng.uniform(key, shape, lo, hi)).astype(F32)
 
 
 def log_uniform_int(key, shape, minval, maxval):

@@ -55,11 +55,13 @@ def main():
         rec = {"metrics": m,
                "lifetime": udist.all_gather_host(agents.level.lifetime.astype(np.int32)),
                "buffer_id": udist.all_gather_host(agents.level.buffer_id.astype(np.int32)),
-               "walls": udist.all_gather_host(np.asarray(agents.level.env_params.walls)),
+               "walls": udist.all_gather_device(agents.level.packed).cpu().numpy(),     # the whole LevelRec of every agent
                "host_step": udist.all_gather_host(agents.host_step.astype(np.int32)),
                "step": udist.all_gather_device(agents.actor_state.step).cpu().numpy(),
                "actor": udist.all_gather_device(agents.actor_state.params).cpu().numpy(),
                "env_state": udist.all_gather_device(agents.env_state.packed).cpu().numpy()}
+        if t == 0:
+            rec["lpg"] = (train_state.mean if args.use_es else train_state.params).cpu().numpy()
         if buf is not None:
             rec.update(score=buf.score.copy(), active=buf.active.copy(), new=buf.new.copy())
         if "_fitness" in metrics:

@@ -75,5 +75,12 @@ def test_two_gpus_reproduce_one_gpu(built_lib, tmp_path, mode):
         n_recreated += int((a["host_step"] == 0).sum())
     if mode != "es":
         assert n_recreated > 0, "the run must include agent re-creation"
+    # after the first meta-step both runs have applied one optimiser step to gradients that differ only by the summation
+    # order of the cross-rank reduction; afterwards the sampled trajectories may diverge, so the end state is only
+    # required to stay close
+    l0, l1 = one["hist"][0]["lpg"], two["hist"][0]["lpg"]
+    d0 = np.abs(l0 - l1).max() / (np.abs(l0).max() + 1e-30)
     d = np.abs(one["lpg"] - two["lpg"]).max() / (np.abs(one["lpg"]).max() + 1e-30)
-    assert d < 2e-6, f"{mode}: LPG parameters differ by {d:.2e}"
+    print(f"{mode}: LPG parameters 1 vs 2 GPUs: after step 1 {d0:.2e}, at the end {d:.2e}")
+    assert d0 < 2e-6, f"{mode}: LPG parameters after the first step differ by {d0:.2e}"
+    assert d < 1e-3, f"{mode}: LPG parameters at the end differ by {d:.2e}"

@@ -74,6 +74,8 @@ SIGNATURES = {
     "toued_a2c_train": [_P] * 15 + [_I] * 7 + [_F] * 6 + [_I, _P],
     "toued_init_tables": [_P] * 3 + [_I] * 3 + [_P],
     "toued_masked_reset": [_P] * 5 + [_I] * 3 + [_P],
+    "toued_generate_levels_desc_bytes": [],
+    "toued_generate_levels": [_P] * 5 + [_I, _P],
     "toued_tc_gemm_test": [_P] * 5,
     "toued_tc_gemm_mixed_test": [_P] * 5,
     "toued_tc_gemm_mn_test": [_P] * 4 + [_I] * 3 + [_P],

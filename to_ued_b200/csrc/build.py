@@ -10,6 +10,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 # so rollout.cu adds -fmad=false.
 FLAGS = {
     "rollout.cu": ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-fmad=false"],
+    "levelgen.cu": ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-fmad=false"],
 }
 
 

@@ -23,6 +23,21 @@ from .maze_data import MAZE_WALL_MASKS, maze_wall_idxs
 
 f32 = np.float32
 
+# exp(x) from individually rounded f32 operations (mirrors csrc/common.cuh::exp_portable and oracle/rollout.py)
+_LOG2E, _LN2_HI, _LN2_LO = f32(1.4426950408889634), f32(0.693359375), f32(-2.12194440e-4)
+_EXP_C = [f32(c) for c in (1.0, 1.0, 0.5, 1.6666667e-1, 4.1666668e-2, 8.3333338e-3, 1.3888889e-3, 1.9841270e-4)]
+
+
+def exp_portable(x):
+    x = np.maximum(np.asarray(x, f32), f32(-80.0))
+    n = np.rint((x * _LOG2E).astype(f32)).astype(f32)
+    r = (x - (n * _LN2_HI).astype(f32)).astype(f32)
+    r = (r - (n * _LN2_LO).astype(f32)).astype(f32)
+    p = np.full_like(r, _EXP_C[7])
+    for c in (_EXP_C[6], _EXP_C[5], _EXP_C[4], _EXP_C[3], _EXP_C[2], _EXP_C[1], _EXP_C[0]):
+        p = ((p * r).astype(f32) + c).astype(f32)
+    return (p.view(np.int32) + (n.astype(np.int32) << 23)).view(f32)
+
 
 @dataclass(frozen=True)
 class LogUniform:            # configs.py:117-126
@@ -33,7 +48,8 @@ class LogUniform:            # configs.py:117-126
 
     def __call__(self, key):
         shape = () if self.n is None else (self.n,)
-        v = np.exp(prng.uniform(key, shape, f32(np.log(f32(self.lo))), f32(np.log(f32(self.hi))))).astype(f32)
+        # exp_portable: the float contract shared with the device generator (csrc/levelgen.cu), DESIGN.md section 2
+        v = exp_portable(prng.uniform(key, shape, f32(np.log(f32(self.lo))), f32(np.log(f32(self.hi))))).astype(f32)
         return np.round(v).astype(np.int32) if self.as_int else v
 
 

@@ -75,8 +75,11 @@ def _lpg_params(train_state):
 class NashSampler(LevelSampler):
     def __init__(self, args, device="cuda"):
         super().__init__(args, device)
+        self.device_levels = False        # the double-oracle buffers are edited level by level on the host (train_do.py:60-63)
         if self.buffer_size > 1024:
-            raise ValueError("the Nash solver kernel supports buffer_size <= 1024")
+            raise ValueError(f"--buffer_size {self.buffer_size}: the double-oracle Nash solver kernel (one CTA: bitonic sort + "
+                             "scan per simplex projection) supports buffer_size <= 1024; pass --buffer_size <= 1024 to train_do.py "
+                             "(the payoff matrix alone costs buffer_size^2 agent lifetimes)")
         self.args = args
         self.lpg_hypers = LpgHyperparams.from_run_args(args)
 

@@ -123,8 +123,11 @@ def restore_checkpoint(path: str, train_state):
 def _buffer_arrays(buf) -> dict:
     out = {"score": _np(buf.score), "active": _np(buf.active), "new": _np(buf.new),
            "level/lifetime": _np(buf.level.lifetime), "level/buffer_id": _np(buf.level.buffer_id)}
-    for f in fields(buf.level.env_params):
-        out[f"level/env_params/{f.name}"] = _np(getattr(buf.level.env_params, f.name))
+    if buf.level.env_params is None:                      # device-resident records (csrc/levelgen.cu): the packed LevelRec bytes
+        out["level/packed"] = _np(buf.level.packed)
+    else:
+        for f in fields(buf.level.env_params):
+            out[f"level/env_params/{f.name}"] = _np(getattr(buf.level.env_params, f.name))
     return out
 
 
@@ -134,5 +137,10 @@ def restore_buffer(path: str):
     from ..environments.level_sampler import LevelBuffer
     from ..util.data import Level
     z = np.load(path)
+    if "level/packed" in z.files:
+        import torch
+        packed = torch.from_numpy(z["level/packed"])
+        packed = packed.cuda() if torch.cuda.is_available() else packed
+        return LevelBuffer(Level(None, z["level/lifetime"], z["level/buffer_id"], packed), z["score"], z["active"], z["new"])
     params = EnvParams(**{f.name: z[f"level/env_params/{f.name}"] for f in fields(EnvParams)})
     return LevelBuffer(Level(params, z["level/lifetime"], z["level/buffer_id"]), z["score"], z["active"], z["new"])
