@@ -26,6 +26,7 @@ VARIANTS = {
     # random delays in front of every mbarrier wait: schedule fuzzing of the warp-specialised kernels
     "fuzz": ["-DTOUED_FUZZ=1"],
     "fuzz_old": ["-DTOUED_FUZZ=1", "-DTOUED_XTILE_OLD=1"],
+    "bwd16": ["-DBT_EW=16"],                 # 16 epilogue warps in gru_backward_tc (measured slower, see the kernel's header)
     "old": ["-DTOUED_XTILE_OLD=1"],
     "probe_old": ["-DTOUED_RACE_PROBE=1", "-DTOUED_XTILE_OLD=1"],      # the round-1 x-tile writer (set 0)
 }

@@ -21,7 +21,18 @@
 #include "../../include/toued.h"
 
 constexpr int BT_M = 128;
-constexpr int BT_THREADS = 352;            // 8 epilogue warps + TMA-load warp + MMA warp + TMA-store warp
+// Epilogue warps: warp w owns TMEM lanes [32 (w & 3), +32) and the unit slice (w >> 2) of every 64-unit block.
+// BT_EW = 8 (two 32-unit halves, 168 registers) is the production geometry.  BT_EW = 16 (four 16-unit quarters, one K-step
+// of the A stage each; library variant "bwd16") was measured in round 2: correct, but 5.96 instead of 4.24 ms per meta-step
+// -- at 608 threads the kernel is capped at 96 registers and spills 284 B per thread in the chunk loop, and four warps per
+// TMEM quadrant queue on the same tcgen05.ld port.  More warps do not buy latency hiding here; fewer instructions would.
+#ifndef BT_EW
+#define BT_EW 8
+#endif
+constexpr int BT_NQ = BT_EW / 4;                 // unit slices per 64-unit block (2 halves or 4 quarters)
+constexpr int BT_NC = 8 / BT_NQ;                 // 8-unit chunks per thread and unit block (4 or 2)
+constexpr int BT_THREADS = (BT_EW + 3) * 32;     // epilogue warps + TMA-load warp + MMA warp + TMA-store warp
+static_assert(BT_EW == 8 || BT_EW == 16, "8 or 16 epilogue warps");
 constexpr int BT_ACHUNK = BT_M * 128;            // 16 KB: [128 rows][64 bf16]
 constexpr int BT_ASTAGE = 6 * BT_ACHUNK;         // dG_r, dG_z, dG_hn, cz_hi, cz_lo, dG_an (store only)
 constexpr int BT_BCHUNK = LPG_H * 128;           // 32 KB: [256 units][64 c]
@@ -66,8 +77,8 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
     float* swp = reinterpret_cast<float*>(sI + BT_ICHUNK);      // [256]
     float* sWy = swp + LPG_H;                                   // [256][8]
     float* sWi = sWy + LPG_H * LPG_Y;                           // [256 units][8]: Wi rows 3, 4 x gates (r, z, n), 2 pad
-    float* sdx = sWi + LPG_H * 8;                               // [128][2]
-    unsigned char* ssign = reinterpret_cast<unsigned char*>(sdx + BT_M * 2);   // [16 chunks][256 threads]: relu'(h_t) bits
+    float* sdx = sWi + LPG_H * 8;                               // [BT_NQ - 1][128][2]
+    unsigned char* ssign = reinterpret_cast<unsigned char*>(sdx + BT_M * 2 * (BT_NQ - 1));   // [4 BT_NC chunks][epilogue threads]: relu'(h_t) bits
     __shared__ __align__(8) uint64_t b_full[BT_NSB], b_empty[BT_NSB], k_full[4], a_empty, q_full;
     __shared__ uint32_t tmem_base_s;
 
@@ -81,7 +92,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
         mbar_init(&a_empty, 2); mbar_init(&q_full, 1);
         mbar_fence_init();
     }
-    if (warp == 9) tmem_alloc(&tmem_base_s, 512);
+    if (warp == BT_EW + 1) tmem_alloc(&tmem_base_s, 512);
     for (int i = tid; i < LPG_H; i += BT_THREADS) swp[i] = lpg[o.w_pi + i];
     for (int i = tid; i < LPG_H * LPG_Y; i += BT_THREADS) sWy[i] = lpg[o.W_y + i];
     for (int i = tid; i < LPG_H * 8; i += BT_THREADS) {
@@ -98,7 +109,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp == 8) {
+    if (warp == BT_EW) {
         // ===================== TMA producer: Wh chunks in (unit block, gate) order ====================
         if (lane == 0) {
             uint32_t it = 0;
@@ -111,7 +122,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                         bulk_g2s(sB + s * BT_BCHUNK, whb_img + (size_t)(g * 4 + ub) * BT_BCHUNK, BT_BCHUNK, &b_full[s]);
                     }
         }
-    } else if (warp == 9) {
+    } else if (warp == BT_EW + 1) {
         // ===================== MMA issuer =============================================================
         // The whole warp walks the loop (all lanes wait on the barriers); one elected lane issues (tc.cuh::elect_one).
         {
@@ -137,7 +148,9 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                     }
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        const int ks = ((kk & 1) << 1) | (kk >> 1);      // 0, 2, 1, 3: the two unit halves progress together
+                        // K-steps in the order the epilogue completes them: with two unit halves 0, 2, 1, 3 (the halves
+                        // progress together), with four quarters 0, 1, 2, 3 (all four finish at the same time)
+                        const int ks = BT_NQ == 2 ? (((kk & 1) << 1) | (kk >> 1)) : kk;
                         mbar_wait(&k_full[ks], ait & 1);
                         tc_fence_after();
                         if (mma && elect_one()) {
@@ -163,7 +176,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                 }
             }
         }
-    } else if (warp == 10) {
+    } else if (warp == BT_EW + 2) {
         // ===================== TMA store warp: dG tiles of every unit block -> token-tile image ==========
         // The SW128 chunks in smem ARE the image's 8 KB sub-tiles of the weight-gradient GEMM, so they leave as
         // full-line bulk stores.  A warp of its own: waiting for the stores to finish reading the stage must not
@@ -192,7 +205,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
             bulk_wait_all();
         }
     } else {
-        // ===================== epilogue / producer-of-A warps 0..7 =====================================
+        // ===================== epilogue / producer-of-A warps 0 .. BT_EW-1 ==============================
         const int q = warp & 3, hf = warp >> 2;
         const int rl = q * 32 + lane;
         const int row = row0 + rl;
@@ -210,7 +223,7 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
         const size_t tstride = R32 * 32 * LPG_H;                 // RB32 elements per timestep
         auto issue_fac = [&](int t_, int ub_, int c8_) {
             FacLoads l;
-            const size_t base = rb32_index((size_t)t_, R32, rsafe, ub_ * 64 + hf * 32 + c8_ * 8);
+            const size_t base = rb32_index((size_t)t_, R32, rsafe, ub_ * 64 + hf * (64 / BT_NQ) + c8_ * 8);
             l.r = *reinterpret_cast<const uint4*>(fac + base);
             l.z = *reinterpret_cast<const uint4*>(fac + gs + base);
             l.n = *reinterpret_cast<const uint4*>(fac + 2 * gs + base);
@@ -230,16 +243,17 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
             r.dn_hp = t_ + 1 < L ? done[((size_t)n_ag * L + t_) * W + w_ag] : (uint8_t)1;   // the cell at t consumed (1 - done_t) h_{t+1}
             return r;
         };
-        // relu'(h_0) bits of this thread's 16 chunks (later steps get theirs from the h' load one step earlier)
-        const int et = tid;                                      // 0..255 among the epilogue warps
-        for (int i = 0; i < 16; ++i) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(h16 + rb32_index(0, R32, rsafe, (i >> 2) * 64 + hf * 32 + (i & 3) * 8));
+        // relu'(h_0) bits of this thread's 4 BT_NC chunks (later steps get theirs from the h' load one step earlier)
+        const int et = tid;                                      // index among the epilogue threads
+        constexpr int ET = BT_EW * 32;
+        for (int i = 0; i < 4 * BT_NC; ++i) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(h16 + rb32_index(0, R32, rsafe, (i / BT_NC) * 64 + hf * (64 / BT_NQ) + (i % BT_NC) * 8));
             float v[8];
             unpack8h(raw, v);
             unsigned b = 0;
 #pragma unroll
             for (int e = 0; e < 8; ++e) b |= (v[e] > 0.0f ? 1u : 0u) << e;
-            ssign[i * 256 + et] = (unsigned char)b;
+            ssign[i * ET + et] = (unsigned char)b;
         }
         FacLoads nxt = issue_fac(0, 0, 0);
         RowLoads rnx = issue_row(0);
@@ -271,16 +285,16 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
             const uint32_t p_addr = tmem_base + ((t - 1) & 1) * 256 + ((uint32_t)(q * 32) << 16);
             float dx3 = 0.f, dx4 = 0.f;
             for (int ub = 0; ub < 4; ++ub) {
-                const int ubase = ub * 64 + hf * 32;                 // first of this thread's 32 units
+                const int ubase = ub * 64 + hf * (64 / BT_NQ);       // first of this thread's 64 / BT_NQ units
 #pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {
+                for (int c8 = 0; c8 < BT_NC; ++c8) {
                     const int u0 = ubase + c8 * 8;
                     float carry[8];
                     if (t > 0) tmem_ld8(p_addr + u0, carry);
                     const FacLoads cur = nxt;
                     {   // prefetch the next chunk (next c8, else next unit block, else next timestep)
                         int t2 = t, ub2 = ub, c2 = c8 + 1;
-                        if (c2 == 4) { c2 = 0; ++ub2; if (ub2 == 4) { ub2 = 0; ++t2; } }
+                        if (c2 == BT_NC) { c2 = 0; ++ub2; if (ub2 == 4) { ub2 = 0; ++t2; } }
                         if (t2 < L) nxt = issue_fac(t2, ub2, c2);
                     }
                     if (t > 0) tmem_ld_wait();
@@ -291,13 +305,13 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                     float gr_[8], zz[8], gn_[8], hn_[8], hx[8];
                     unpack8h(cur.r, gr_); unpack8h(cur.z, zz); unpack8h(cur.n, gn_);
                     unpack8h(cur.hn, hn_); unpack8h(cur.hx, hx);
-                    const int ci = ub * 4 + c8;
-                    const unsigned sg = ssign[ci * 256 + et];              // relu'(h_t)
+                    const int ci = ub * BT_NC + c8;
+                    const unsigned sg = ssign[ci * ET + et];               // relu'(h_t)
                     {
                         unsigned b = 0;
 #pragma unroll
                         for (int e = 0; e < 8; ++e) b |= (hx[e] > 0.0f ? 1u : 0u) << e;
-                        ssign[ci * 256 + et] = (unsigned char)b;          // relu'(h_{t+1}) for the next step
+                        ssign[ci * ET + et] = (unsigned char)b;           // relu'(h_{t+1}) for the next step
                     }
                     float gr[8], gz[8], ghn[8], gan[8], czh[8], czl[8];
 #pragma unroll
@@ -332,36 +346,41 @@ gru_backward_tc_kernel(const uint8_t* __restrict__ done, const float* __restrict
                     // the MMAs and the image stores of the previous unit block must have consumed the A stage
                     // (they finished long ago: this chunk's math alone takes longer)
                     if (c8 == 0 && ait > 0) mbar_wait(&a_empty, (ait & 1) ^ 1);
-                    const uint32_t so = sA_u32 + sw128_offset(BT_M, rl, hf * 32 + c8 * 8);
+                    const uint32_t so = sA_u32 + sw128_offset(BT_M, rl, hf * (64 / BT_NQ) + c8 * 8);
                     st_shared_v4(so + 0 * BT_ACHUNK, pack8h_sat(gr));
                     st_shared_v4(so + 1 * BT_ACHUNK, pack8h_sat(gz));
                     st_shared_v4(so + 2 * BT_ACHUNK, pack8h_sat(ghn));
                     st_shared_v4(so + 3 * BT_ACHUNK, pack8h_sat(czh));
                     st_shared_v4(so + 4 * BT_ACHUNK, pack8h_sat(czl));
                     st_shared_v4(so + 5 * BT_ACHUNK, pack8h_sat(gan));
-                    if (c8 & 1) {                                  // K-step 2 hf + (c8 >> 1) of this unit block is complete
+                    if (c8 & 1) {                                  // K-step hf * BT_NC / 2 + (c8 >> 1) of this unit block is complete
                         fence_proxy_async_smem();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&k_full[2 * hf + (c8 >> 1)]);
+                        if (lane == 0) mbar_arrive(&k_full[hf * (BT_NC / 2) + (c8 >> 1)]);
                     }
                 }
                 ++ait;
             }
-            // d pyt / d pyt1: combine the two unit halves of the row
-            if (hf == 1) { sdx[rl * 2] = dx3; sdx[rl * 2 + 1] = dx4; }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (hf == 0 && rv) *reinterpret_cast<float2*>(dx + ((size_t)t * R + row) * 2) = make_float2(dx3 + sdx[rl * 2], dx4 + sdx[rl * 2 + 1]);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // d pyt / d pyt1: combine the unit slices of the row (fixed order)
+            if (hf > 0) { sdx[((hf - 1) * BT_M + rl) * 2] = dx3; sdx[((hf - 1) * BT_M + rl) * 2 + 1] = dx4; }
+            asm volatile("bar.sync 1, %0;" ::"n"(BT_EW * 32) : "memory");
+            if (hf == 0 && rv) {
+#pragma unroll
+                for (int h2 = 0; h2 < BT_NQ - 1; ++h2) { dx3 += sdx[(h2 * BT_M + rl) * 2]; dx4 += sdx[(h2 * BT_M + rl) * 2 + 1]; }
+                *reinterpret_cast<float2*>(dx + ((size_t)t * R + row) * 2) = make_float2(dx3, dx4);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(BT_EW * 32) : "memory");
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, 512);
+    if (warp == BT_EW + 1) tmem_dealloc(tmem_base, 512);
 }
 
 static size_t gru_bwd_tc_smem() {
-    return BT_ASTAGE + BT_NSB * BT_BCHUNK + BT_ICHUNK + sizeof(float) * (LPG_H + LPG_H * LPG_Y + LPG_H * 8 + BT_M * 2) + 16 * 256 + 1024;
+    return BT_ASTAGE + BT_NSB * BT_BCHUNK + BT_ICHUNK + sizeof(float) * (LPG_H + LPG_H * LPG_Y + LPG_H * 8 + BT_M * 2 * (BT_NQ - 1)) +
+           4 * BT_NC * BT_EW * 32 + 1024;
 }
 
 extern "C" int toued_gru_backward_tc(const uint8_t* done, const float* lpg_params, const void* whb_img,
