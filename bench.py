@@ -550,7 +550,7 @@ def run_ours(a):
 BYTES_PER_TOKEN = {"toued_gru_forward_tc": 32.0 + 4 * 512 + 512 + 512 + 36,
                    "toued_gru_backward_tc": 4 * 512 + 512 + 72 + 2048 + 40.0,
                    "toued_lpg_wgrad_tc": 2048 + 512 + 512 + 128 + 36.0}
-NCU_SUMMARY = "r01_ncu_summary.json"
+NCU_SUMMARY = "r02_ncu_summary.json"
 
 
 def main():
