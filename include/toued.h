@@ -268,8 +268,9 @@ int toued_pack_wh_forward(const float* lpg_params, void* wh_img, int lifetime_co
 /* Tensor-core version of toued_gru_forward (models/lpg.py:11-30,77-84): fp16 operands, fp32
  * accumulation in TMEM.  Saved for the reverse pass (NULL to skip):
  *   h16   f16, RB32 layout [L][ceil(R/32)][32 chunks][32 rows][8 units] (csrc/tc.cuh::rb32_index)   h_t
- *   fac   f16[4] planes in the same RB32 layout: the gates r, z, n and hn = Whn h' + bhn (the reverse pass
- *         rebuilds its factors from them and takes h' from h16 of step t+1)
+ *   fac   f16 [L][R/32][4 planes][32 chunks][32 rows][8]: the gates r, z, n and hn = Whn h' + bhn as RB32 blocks with
+ *         the planes interleaved per (t, 32-row block); the sign bits of the z plane carry relu'(h_t) (set: h_t <= 0).
+ *         The reverse pass rebuilds its factors from them and takes h' from h16 of step t+1.
  *   hpimg bf16 token-tile image [L*Rp/64][4][64][64] of the masked carry h' used at each step
  * pi_hat / y_hat stay fp32.                                                                        */
 int toued_gru_forward_tc(const float* x, const uint8_t* done, const float* lpg_params, const void* wh_img,

@@ -88,8 +88,12 @@ def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond, n):
             _lib.call("toued_gru_forward_tc", p(tape.x[0]), p(tape.done[0]), p(lpg), p(tape.wh_img), p(tape.h16[0]),
                       p(tape.fac[0]), p(tape.hpimg[0]), p(tape.pi_hat[0]), p(tape.y_hat[0]), n, c.w, c.L, int(cond), s)
             R = n * c.w
-            out[prec] = (tape.pi_hat[0].clone(), tape.y_hat[0].clone(), _from_rb32(tape.h16[0], c.L, R).float(),
-                         torch.stack([_from_rb32(tape.fac[0][i], c.L, R) for i in range(4)]).float())
+            planes = [_fac_plane(tape.fac[0], i, c.L, R) for i in range(4)]
+            # the sign bits of the saved z plane carry relu'(h_t) for the reverse pass: set <=> fp16 h_t <= 0
+            h16_ = _from_rb32(tape.h16[0], c.L, R)
+            assert torch.equal(torch.signbit(planes[1]), h16_ <= 0), "z-plane sign bits != (h16 <= 0)"
+            planes[1] = planes[1].abs()
+            out[prec] = (tape.pi_hat[0].clone(), tape.y_hat[0].clone(), h16_.float(), torch.stack(planes).float())
             out["hpimg"] = tape.hpimg[0].clone()
         else:
             _lib.call("toued_gru_forward", p(tape.x[0]), p(tape.done[0]), p(lpg), p(tape.h[0]), p(tape.gates[0]),
@@ -164,6 +168,13 @@ def test_meta_gradient_tensor_core_path(built_lib, mode, cond, n, w, monkeypatch
     l2 = np.linalg.norm(g - og) / np.linalg.norm(og)
     print(f"[tc {mode}] relative L2 error of the meta-gradient {l2:.2e}")
     assert l2 < 1e-2
+
+
+def _fac_plane(x, i, L, R):
+    """Gate plane i of the saved-gate tensor [L][R/32][4 planes][32 chunks][32 rows][8] (csrc/tc.cuh::fac_index) -> [L][R][256]."""
+    R32 = (R + 31) // 32
+    v = x.reshape(L, R32, 4, 32, 32, 8)[:, :, i].permute(0, 1, 3, 2, 4).reshape(L, R32 * 32, 256)
+    return v[:, :R]
 
 
 def _from_rb32(x, L, R):

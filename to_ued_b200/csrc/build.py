@@ -27,6 +27,8 @@ VARIANTS = {
     "fuzz": ["-DTOUED_FUZZ=1"],
     "fuzz_old": ["-DTOUED_FUZZ=1", "-DTOUED_XTILE_OLD=1"],
     "bwd16": ["-DBT_EW=16"],                 # 16 epilogue warps in gru_backward_tc (measured slower, see the kernel's header)
+    "pf2": ["-DBT_PF_DEPTH=2"],              # gru_backward_tc with two chunks of saved activations in flight per thread
+    "pf": ["-DBT_L2_PREFETCH=1"],            # gru_backward_tc with an L2 bulk prefetch of the next step's saved activations (measured slower)
     "old": ["-DTOUED_XTILE_OLD=1"],
     "probe_old": ["-DTOUED_RACE_PROBE=1", "-DTOUED_XTILE_OLD=1"],      # the round-1 x-tile writer (set 0)
 }

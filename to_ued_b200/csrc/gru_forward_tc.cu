@@ -17,7 +17,8 @@
 //   * Epilogue: two sets of 8 warps (set 0 = even passes / accumulator 0, set 1 = odd passes / accumulator 1; in a set
 //     warp q + 4 hf owns TMEM lanes [32q, 32q + 32) and units [8 hf, 8 hf + 8) of the pass).  tcgen05.ld the
 //     pre-activations and h', flax GRUCell gate math (ex2.approx / rcp.approx), tcgen05.st h_t into the other hidden
-//     buffer, and save h16, the four gate planes (fp16, RB32 layout) and the fp16 token-tile image of the masked carry.
+//     buffer, and save h16, the four gate planes (fp16, RB32 layout; the sign bits of the z plane carry relu'(h_t)) and the
+//     fp16 token-tile image of the masked carry.
 //   * Heads on the tensor cores: relu(h_t) of each pass goes to 8 TMEM columns (ring of 4 tiles) and is the A operand of
 //     a K = 16 MMA against [w_pi | W_y] (fp16 hi / lo, N = 32); the per-step epilogue adds biases and does the softmax.
 //   * The x tile of step s + 2 overwrites the tile step s used: it is written by SET 1 (whose last pass, 15, is the last
@@ -254,7 +255,6 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
         const int rsafe = rv ? row : 0;
         const int n_ag = rsafe / W, w_ag = rsafe % W;
         const size_t R32 = ((size_t)R + 31) >> 5;             // 32-row blocks of the RB32 layout
-        const size_t gs = (size_t)L * R32 * 32 * LPG_H;       // elements per saved factor plane
         const size_t Rp = ((size_t)R + 63) & ~(size_t)63;     // rows padded to the 64-token image blocks
         int cur = 0;
         // initial carry = 0: hidden-state buffer 0 (this thread's columns)
@@ -369,10 +369,19 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                     if (h16) *reinterpret_cast<uint4*>(h16 + so) = hpk;
                     if (fac) {
                         // the reverse pass rebuilds its factors from the gates (and h' from h16 of step t+1)
-                        *reinterpret_cast<uint4*>(fac + so) = pack8(rr);
-                        *reinterpret_cast<uint4*>(fac + gs + so) = pack8(zz);
-                        *reinterpret_cast<uint4*>(fac + 2 * gs + so) = pack8(nn);
-                        *reinterpret_cast<uint4*>(fac + 3 * gs + so) = pack8(hn);
+                        const size_t fo = fac_index((size_t)t, R32, rsafe, u0, 0);      // planes 4096 elements apart
+                        *reinterpret_cast<uint4*>(fac + fo) = pack8(rr);
+                        // z is in [0, 1]: its sign bits carry relu'(h_t) for the reverse pass (set = the fp16 h_t is <= 0)
+                        uint4 zp = pack8(zz);
+                        {
+                            const __half2 zero2 = __float2half2_rn(0.0f);
+                            const __half2* hs2 = reinterpret_cast<const __half2*>(&hpk);
+                            zp.x |= __hle2_mask(hs2[0], zero2) & 0x80008000u; zp.y |= __hle2_mask(hs2[1], zero2) & 0x80008000u;
+                            zp.z |= __hle2_mask(hs2[2], zero2) & 0x80008000u; zp.w |= __hle2_mask(hs2[3], zero2) & 0x80008000u;
+                        }
+                        *reinterpret_cast<uint4*>(fac + fo + 8192) = zp;
+                        *reinterpret_cast<uint4*>(fac + fo + 2 * 8192) = pack8(nn);
+                        *reinterpret_cast<uint4*>(fac + fo + 3 * 8192) = pack8(hn);
                     }
                     if (hpimg) {
                         // h' consumed at step t-1 (= masked h_t): fp16 token-tile image for the weight-gradient GEMM (the very fp16

@@ -39,6 +39,13 @@ __host__ __device__ __forceinline__ size_t rb32_index(size_t t, size_t n_row_blo
     return (((t * n_row_blocks + (size_t)(row >> 5)) * 32 + (size_t)(u >> 3)) << 8) + (size_t)((row & 31) << 3) + (size_t)(u & 7);
 }
 
+// The four saved gate planes (r, z, n, hn) of the tensor-core forward: RB32 blocks with the planes INTERLEAVED per
+// (t, 32-row block): [t][row block][plane][chunk][32 rows][8 units].  (Four separate [L][R]-sized planes put the four
+// loads a reverse-pass thread issues together exactly 160 MiB apart at the BASELINE shape.)
+__host__ __device__ __forceinline__ size_t fac_index(size_t t, size_t n_row_blocks, int row, int u, int plane) {
+    return ((((t * n_row_blocks + (size_t)(row >> 5)) * 4 + (size_t)plane) * 32 + (size_t)(u >> 3)) << 8) + (size_t)((row & 31) << 3) + (size_t)(u & 7);
+}
+
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
@@ -140,6 +147,11 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// global -> L2 prefetch of a contiguous range (bytes: multiple of 16)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
