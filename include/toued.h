@@ -161,6 +161,10 @@ int toued_adam(float* params, const float* grad, float* mu, float* nu, int n, in
  * no host-side state, so the call can be part of a captured CUDA graph (meta/graph.py).               */
 int toued_adam_dev(float* params, const float* grad, float* mu, float* nu, int* count_dev, int n, float lr,
                    float b1, float b2, float eps, void* stream);
+/* models/optim.py:6-11 (--lpg_opt SGD): optax.clip_by_global_norm(max_norm) -> scale(lr) -> scale(-1) on the flat LPG
+ * parameter vector.  sqnorm_scratch f32[1] receives |grad|^2 (fixed-order reduction).                       */
+int toued_sgd_clip(float* params, const float* grad, float* sqnorm_scratch, int n, float lr, float max_norm,
+                   void* stream);
 
 /* ---- A2C antagonist (agents/a2c.py:19-76), used by the algorithmic-regret level score ---------- */
 /* critic_in/out: value tables f32[N][D][8] (column 0).  scalars f32[N][4] = {actor_loss, critic_loss,

@@ -84,6 +84,19 @@ def lpg_meta_grad_train_step(rng, layout: LPGLayout, lpg_flat, ag: AgentTables, 
                 trajectories=rollouts, eval_trajectory=eval_traj, adv=adv, debug=dbg)
 
 
+class SGDClip:
+    """optax.chain(clip_by_global_norm(max_norm), scale(lr), scale(-1)) (models/optim.py:6-11, ``--lpg_opt SGD``);
+    optax.clip_by_global_norm: g if |g| < max_norm else g / |g| * max_norm."""
+
+    def __init__(self, lr, max_norm):
+        self.lr, self.max_norm = lr, max_norm
+
+    def step(self, params, grad):
+        norm = torch.sqrt((grad * grad).sum())
+        g = grad if float(norm) < self.max_norm else grad / norm * self.max_norm
+        return params - self.lr * g
+
+
 class Adam:
     """optax.scale_by_adam(b1=.9, b2=.999, eps=1e-8, eps_root=0) -> scale(lr) -> scale(-1)
     (models/optim.py:12-17; no clipping on this branch, Q9)."""

@@ -63,6 +63,7 @@ SIGNATURES = {
     "toued_lpg_wgrad_tc": [_P] * 9 + [_I] * 4 + [_P],
     "toued_adam": [_P] * 4 + [_I, _I] + [_F] * 4 + [_P],
     "toued_adam_dev": [_P] * 5 + [_I] + [_F] * 4 + [_P],
+    "toued_sgd_clip": [_P] * 3 + [_I, _F, _F, _P],
     "toued_get_nash": [_P] * 5 + [_I] * 4 + [_F, _P],
     "toued_projection_simplex": [_P, _I, _I, _P],
     "toued_es_ask": [_P, _P, _F, _P, _I, _I, _I, _P],
@@ -117,7 +118,7 @@ def stream_ptr():
 
 
 # kernels launched by one call of each entry point (for the bench's gpu_launches count)
-KERNELS_PER_CALL = {"toued_adam_dev": 2, "toued_lpg_wgrad": 3, "toued_init_tables": 2, "toued_lpg_wgrad_tc": 2, "toued_pack_wh_forward": 2, "toued_pack_wh_forward_multi": 2}
+KERNELS_PER_CALL = {"toued_adam_dev": 2, "toued_sgd_clip": 2, "toued_lpg_wgrad": 3, "toued_init_tables": 2, "toued_lpg_wgrad_tc": 2, "toued_pack_wh_forward": 2, "toued_pack_wh_forward_multi": 2}
 LAUNCHES = {}          # entry point -> number of calls since reset_counters()
 GRAPH_KERNELS = [0]    # kernels launched by CUDA-graph replays since reset_counters() (meta/graph.py)
 ENV_STEPS = [0]        # gridworld env-steps simulated by the enqueued rollouts since reset_counters() (bench.py's metric)

@@ -13,6 +13,7 @@
 //                        dWh = h'^T dGh (tiled SGEMM), dWi/dbi/dbhn/heads (streaming), embedding MLP.
 //   toued_reduce_partials  grad[p] (+)= sum_s partial[s][p]
 //   toued_adam           optax.scale_by_adam -> scale(lr) -> scale(-1)  (models/optim.py:12-17, Q9)
+//   toued_sgd_clip       optax.clip_by_global_norm -> scale(lr) -> scale(-1)  (models/optim.py:6-11, --lpg_opt SGD)
 #include "lpg_common.cuh"
 #include "tc.cuh"
 #include "../../include/toued.h"
@@ -622,6 +623,43 @@ extern "C" int toued_adam_dev(float* params, const float* grad, float* mu, float
     adam_dev_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params, grad, mu, nu, count_dev, n, lr, b1, b2, eps);
     TOUED_LAUNCH_CHECK();
     count_incr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(count_dev);
+    TOUED_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// --lpg_opt SGD (models/optim.py:6-11): optax.chain(clip_by_global_norm(max_norm), scale(lr), scale(-1)).
+// One CTA reduces |g|^2 in a fixed order (deterministic), the update kernel reads it back: nothing depends on host state.
+__global__ void __launch_bounds__(1024) sqnorm_kernel(const float* __restrict__ g, int n, float* __restrict__ out) {
+    __shared__ float part[32];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += 1024) s = fmaf(g[i], g[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = part[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) out[0] = s;
+    }
+}
+__global__ void sgd_clip_kernel(float* __restrict__ p, const float* __restrict__ g, const float* __restrict__ sq, int n,
+                                float lr, float max_norm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float norm = sqrtf(sq[0]);
+    // optax.clip_by_global_norm: where(norm < max_norm, g, g / norm * max_norm)
+    const float gi = norm < max_norm ? g[i] : (g[i] / norm) * max_norm;
+    p[i] -= lr * gi;
+}
+extern "C" int toued_sgd_clip(float* params, const float* grad, float* sqnorm_scratch, int n, float lr, float max_norm,
+                              void* stream) {
+    TOUED_CHECK(n > 0 && sqnorm_scratch != nullptr, "toued_sgd_clip: bad arguments");
+    sqnorm_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(grad, n, sqnorm_scratch);
+    TOUED_LAUNCH_CHECK();
+    sgd_clip_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params, grad, sqnorm_scratch, n, lr, max_norm);
     TOUED_LAUNCH_CHECK();
     return 0;
 }

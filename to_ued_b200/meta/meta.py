@@ -17,8 +17,6 @@ def create_lpg_train_state(rng, args, single_env=False, device="cuda"):
                     target_width=args.lpg_target_width, lifetime_conditioning=args.lifetime_conditioning)
     params = lpg_model.init(rng, device=device)
     tx = create_optimizer(args.lpg_opt, args.lpg_learning_rate, args.lpg_max_grad_norm)
-    if tx.name != "Adam":
-        raise NotImplementedError("the LPG optimiser on the B200 path is Adam (the reference default)")
     train_state = LPGTrainState(lpg_model, params, tx)
     if not args.use_es or single_env:
         return train_state

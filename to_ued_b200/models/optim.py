@@ -6,18 +6,33 @@ optax.chain(scale_by_adam(), scale(lr), scale(-1)) (no clipping on this branch, 
 toued_adam on the flat LPG parameter vector."""
 from __future__ import annotations
 
-from dataclasses import dataclass
-
 import torch
 
 from .. import _lib
 
 
-@dataclass
 class SGD:
-    learning_rate: float
-    max_grad_norm: float
-    name: str = "SGD"
+    """optax.chain(clip_by_global_norm(max_grad_norm), scale(lr), scale(-1)) (models/optim.py:6-11).  For the tabular
+    agents the same chain is fused into toued_agent_update; as the LPG optimiser (``--lpg_opt SGD``) it runs in
+    toued_sgd_clip on the flat parameter vector.  The optimiser state keeps Adam's keys so that the captured-graph step
+    and the checkpoint code treat both optimisers alike: ``mu`` is the f32[1] scratch that receives |g|^2."""
+    name = "SGD"
+
+    def __init__(self, learning_rate: float, max_grad_norm: float):
+        self.learning_rate, self.max_grad_norm = learning_rate, max_grad_norm
+
+    def init(self, params: torch.Tensor):
+        return {"mu": torch.zeros(1, dtype=torch.float32, device=params.device),
+                "nu": torch.zeros(1, dtype=torch.float32, device=params.device), "count": 0}
+
+    def update_(self, params: torch.Tensor, grad: torch.Tensor, state: dict) -> dict:
+        _lib.call("toued_sgd_clip", _lib.ptr(params), _lib.ptr(grad), _lib.ptr(state["mu"]), params.numel(),
+                  float(self.learning_rate), float(self.max_grad_norm), _lib.stream_ptr())
+        return {"mu": state["mu"], "nu": state["nu"], "count": state["count"] + 1}
+
+    def update_dev_(self, params, grad, mu, nu, count_dev) -> None:
+        _lib.call("toued_sgd_clip", _lib.ptr(params), _lib.ptr(grad), _lib.ptr(mu), params.numel(),
+                  float(self.learning_rate), float(self.max_grad_norm), _lib.stream_ptr())
 
 
 class Adam:
