@@ -212,6 +212,23 @@ int toued_es_adam(const float* grad_sum, float* mean, float* m, float* v, int po
                   void* stream);
 
 /* ---- device level generator (environments/gridworld/configs.py:12-57, environments.py:23-38) -------- */
+/* Prioritised Level Replay index work on the device (environments/level_sampler.py:183-234, 331-408), one CTA.
+ * The level buffer is score f32[B], active u8[B], is_new u8[B] (B <= 8192), updated in place.
+ * toued_plr_reset_lowest = _reset_lowest_scoring (:331-353, quirk Q3 reproduced): writes the minimum_new ids of the
+ *   lowest-scoring levels to reset_ids i32[minimum_new] and resets their score / flags; the caller regenerates those
+ *   level records (toued_generate_levels with buffer_ids = reset_ids).
+ * toued_plr_select = the buffer update with the regret scores of the terminated agents, _replay_from_buffer with
+ *   score_transform "rank", _sample_random_from_buffer, the Bernoulli(p_replay) replay count, the permutation and the
+ *   final choice (:183-234).  (key0, key1) = the sampler's rng right before split(rng, 3) at :201; old_ids /
+ *   terminated / new_scores are those of the GLOBAL batch (n_agents <= B); shuffle_rounds =
+ *   ceil(3 ln n / ln(2^32 - 1)) (jax _shuffle).  Writes new_ids i32[n_agents] and marks them active.
+ * Float contract of the rank transform: exp_portable(clamp(score / temperature, -80, 80)), left-to-right fp32 sum.  */
+int toued_plr_reset_lowest(float* score, uint8_t* active, uint8_t* is_new, int buffer_size, int minimum_new,
+                           int* reset_ids, void* stream);
+int toued_plr_select(uint32_t key0, uint32_t key1, float* score, uint8_t* active, uint8_t* is_new, int buffer_size,
+                     const int* old_ids, const uint8_t* terminated, const float* new_scores, int n_agents,
+                     float p_replay, float temperature, int shuffle_rounds, int* new_ids, void* stream);
+
 /* One LevelRec per key: keys u32[n][2] are the per-level keys the reference passes to reset_env_params
  * (split(rng, n)); gen_desc is the mode description built by the host (to_ued_b200/environments/gridworld/levelgen.py,
  * toued_generate_levels_desc_bytes() bytes); buffer_ids i32[n] or NULL (0); lifetimes_out i32[n] or NULL.

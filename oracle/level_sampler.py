@@ -24,13 +24,25 @@ def reset_lowest_scoring(score, active, new, minimum_new):
     return reset_ids, score2, active2, new2
 
 
+def replay_scores(score, invalid, temperature=1.0):
+    """exp(score / T) masked and normalised (level_sampler.py:365-370).  Float contract shared with the device kernel
+    (csrc/plr.cu) and the host path, since these floats can create or break ties of the ranking: ``exp_portable`` on the
+    argument clamped to [-80, 80] (the reference's jnp.exp overflows beyond that anyway), a LEFT-TO-RIGHT fp32 sum,
+    IEEE division."""
+    from .rollout import exp_portable
+    F32 = np.float32
+    x = np.clip((np.asarray(score, F32) / F32(temperature)).astype(F32), F32(-80), F32(80))
+    s = np.where(invalid, F32(0), exp_portable(x)).astype(F32)
+    total = np.cumsum(s, dtype=F32)[-1]                      # sequential accumulation
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return (s / total).astype(F32)
+
+
 def replay_ids(score, active, new, batch_size, temperature=1.0):
     """rank transform: flip(argsort(p))[:batch]"""
     B = len(score)
     invalid = new | active
-    s = np.exp(score / np.float32(temperature)).astype(np.float32)
-    s = np.where(invalid, np.float32(0), s)
-    s = (s / s.sum(dtype=np.float32)).astype(np.float32)
+    s = replay_scores(score, invalid, temperature)
     p = np.where(B - invalid.sum() < batch_size, np.ones_like(s), s)
     return np.flip(np.argsort(p, kind="stable"))[:batch_size]
 

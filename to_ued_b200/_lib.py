@@ -77,6 +77,8 @@ SIGNATURES = {
     "toued_masked_reset": [_P] * 5 + [_I] * 3 + [_P],
     "toued_generate_levels_desc_bytes": [],
     "toued_generate_levels": [_P] * 5 + [_I, _P],
+    "toued_plr_reset_lowest": [_P] * 3 + [_I, _I, _P, _P],
+    "toued_plr_select": [C.c_uint32, C.c_uint32] + [_P] * 3 + [_I] + [_P] * 3 + [_I, _F, _F, _I, _P, _P],
     "toued_tc_gemm_test": [_P] * 5,
     "toued_tc_gemm_mixed_test": [_P] * 5,
     "toued_tc_gemm_mn_test": [_P] * 4 + [_I] * 3 + [_P],
