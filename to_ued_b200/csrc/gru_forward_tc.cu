@@ -295,7 +295,12 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
             }
             // mask for the NEXT processed step (t-1): its carry is zero where done[t-1]
             const bool zero_next = (t > 0) && done[((size_t)n_ag * L + (t - 1)) * W + w_ag];
-            const size_t tokbase = rb32_index((size_t)t, R32, rsafe, 0);
+            // per-step output pointers (64-bit address arithmetic once per step; the passes add 32-bit offsets)
+            __half* const h16_t = h16 + rb32_index((size_t)t, R32, rsafe, 0);
+            __half* const fac_t = fac ? fac + fac_index((size_t)t, R32, rsafe, 0, 0) : nullptr;
+            const size_t hp_tok = (size_t)(t > 0 ? t - 1 : 0) * Rp + row;              // token of the masked carry h' consumed at step t-1
+            unsigned char* const hp_t = hpimg ? hpimg + (((hp_tok >> 6) * 4) << 13) + (hp_tok & 63) * 128 : nullptr;
+            const uint32_t hp_r7 = (uint32_t)(hp_tok & 7);
             for (int p = set; p < FT_NPASS; p += 2) {
                 const uint32_t it = (uint32_t)step * FT_NPASS + p;
                 const int a = set;
@@ -365,12 +370,12 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                     if (lane == 0) mbar_arrive(&stage_full[sb]);
                 }
                 if (rv) {
-                    const size_t so = tokbase + ((size_t)(u0 >> 3) << 8);          // RB32: chunk stride 256 elements
-                    if (h16) *reinterpret_cast<uint4*>(h16 + so) = hpk;
+                    const uint32_t so = (uint32_t)(u0 >> 3) << 8;                   // RB32: chunk stride 256 elements
+                    if (h16) *reinterpret_cast<uint4*>(h16_t + so) = hpk;
                     if (fac) {
                         // the reverse pass rebuilds its factors from the gates (and h' from h16 of step t+1)
-                        const size_t fo = fac_index((size_t)t, R32, rsafe, u0, 0);      // planes 4096 elements apart
-                        *reinterpret_cast<uint4*>(fac + fo) = pack8(rr);
+                        __half* const fo = fac_t + so;                              // planes 8192 elements apart (tc.cuh::fac_index)
+                        *reinterpret_cast<uint4*>(fo) = pack8(rr);
                         // z is in [0, 1]: its sign bits carry relu'(h_t) for the reverse pass (set = the fp16 h_t is <= 0)
                         uint4 zp = pack8(zz);
                         {
@@ -379,15 +384,15 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                             zp.x |= __hle2_mask(hs2[0], zero2) & 0x80008000u; zp.y |= __hle2_mask(hs2[1], zero2) & 0x80008000u;
                             zp.z |= __hle2_mask(hs2[2], zero2) & 0x80008000u; zp.w |= __hle2_mask(hs2[3], zero2) & 0x80008000u;
                         }
-                        *reinterpret_cast<uint4*>(fac + fo + 8192) = zp;
-                        *reinterpret_cast<uint4*>(fac + fo + 2 * 8192) = pack8(nn);
-                        *reinterpret_cast<uint4*>(fac + fo + 3 * 8192) = pack8(hn);
+                        *reinterpret_cast<uint4*>(fo + 8192) = zp;
+                        *reinterpret_cast<uint4*>(fo + 2 * 8192) = pack8(nn);
+                        *reinterpret_cast<uint4*>(fo + 3 * 8192) = pack8(hn);
                     }
                     if (hpimg) {
                         // h' consumed at step t-1 (= masked h_t): fp16 token-tile image for the weight-gradient GEMM (the very fp16
                         // values the recurrence used: no second rounding)
-                        if (t > 0)
-                            *reinterpret_cast<uint4*>(hpimg + tile_img_offset((size_t)(t - 1) * Rp + row, 4, u0)) =
+                        if (t > 0)       // tile_img_offset(hp_tok, 4, u0) with the per-step part hoisted
+                            *reinterpret_cast<uint4*>(hp_t + ((uint32_t)(u0 >> 6) << 13) + ((((uint32_t)(u0 & 63) >> 3) ^ hp_r7) << 4)) =
                                 zero_next ? make_uint4(0u, 0u, 0u, 0u) : hpk;
                         if (t == L - 1)
                             *reinterpret_cast<uint4*>(hpimg + tile_img_offset((size_t)t * Rp + row, 4, u0)) = make_uint4(0u, 0u, 0u, 0u);

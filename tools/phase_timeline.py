@@ -20,7 +20,7 @@ from to_ued_b200.meta.meta import create_lpg_train_state, make_lpg_train_step  #
 
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-    args = parse_args(["--env_mode", "all_shortlife", "--num_agents", "512", "--num_mini_batches",
+    args = parse_args(["--env_mode", "all_shortlife", "--num_agents", os.environ.get("TOUED_AGENTS", "512"), "--num_mini_batches",
                        os.environ.get("TOUED_BENCH_MINI_BATCHES", "2")])
     rng = prng.PRNGKey(args.seed)
     rng, lpg_rng, buffer_rng = prng.split(rng, 3)
