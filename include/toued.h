@@ -88,14 +88,17 @@ int toued_gru_forward(const float* x, const uint8_t* done, const float* lpg_para
  *                        critic_entropy}
  * toued_agent_update / toued_agent_backward need a temporary of 52 B x min(W*L, D) per agent for the duration of the
  * launch: run_scratch, f32[toued_agent_scratch_floats(N, W, L, D)], provided by the caller like every other buffer
- * (calls that may run concurrently on different streams need distinct scratch buffers).               */
+ * (calls that may run concurrently on different streams need distinct scratch buffers).
+ * tables_precopied != 0: actor_out / critic_out already hold a copy of actor_in / critic_in (made by the caller, e.g. on
+ * a side stream next to the LPG forward); the kernel then writes the touched rows only.                  */
 int toued_agent_scratch_floats(int n_agents, int n_workers, int rollout_len, int obs_dim);
 int toued_agent_update(const int32_t* obs, const uint8_t* action, const uint16_t* sorted_tok,
                        const float* pi_hat, const float* y_hat, const float* actor_in,
                        const float* critic_in, float* actor_out, float* critic_out,
                        const void* levels, int32_t* step, float* scalars, int n_agents,
                        int n_workers, int rollout_len, int obs_dim, float lr_actor, float lr_critic,
-                       float max_grad_norm, float agent_target_coeff, float* run_scratch, void* stream);
+                       float max_grad_norm, float agent_target_coeff, int tables_precopied, float* run_scratch,
+                       void* stream);
 
 /* ---- meta-gradient (meta/train.py:14-130): what the reference gets from jax.grad ---------------- */
 

@@ -43,7 +43,7 @@ SIGNATURES = {
     "toued_sort_tokens": [_P] * 2 + [_I] * 3 + [_P],
     "toued_lpg_prepare": [_P] * 11 + [_I] * 6 + [_P],
     "toued_gru_forward": [_P] * 7 + [_I] * 5 + [_P],
-    "toued_agent_update": [_P] * 12 + [_I] * 4 + [_F] * 4 + [_P, _P],
+    "toued_agent_update": [_P] * 12 + [_I] * 4 + [_F] * 4 + [_I, _P, _P],
     "toued_agent_scratch_floats": [_I] * 4,
     "toued_meta_loss": [_P] * 10 + [_I] * 5 + [_F] * 3 + [_I, _P],
     "toued_agent_backward": [_P] * 14 + [_I] * 4 + [_F] * 9 + [_P, _P],

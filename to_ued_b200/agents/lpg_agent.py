@@ -130,6 +130,12 @@ def lpg_agent_train_step(k, tape: Tape, levels, step, lpg_params, lifetime_condi
     with torch.cuda.stream(side):
         side.wait_event(ev_roll)
         _lib.call("toued_sort_tokens", p(tape.obs[r]), p(tape.sorted_tok[r]), N, W, L, _lib.stream_ptr())
+        # the dense copy theta_k -> theta_{k+1} (the update changes only touched rows) depends on nothing but theta_k:
+        # it rides on the side stream next to the LPG forward instead of heading the agent-update kernel
+        precopied = bool(to_ued_b200.SIDE_STREAMS)
+        if precopied:
+            tape.actor[t1].copy_(tape.actor[t0])
+            tape.critic[t1].copy_(tape.critic[t0])
         ev_sort.record(side)
     tape.step_in[a].copy_(step)
     _lib.call("toued_lpg_prepare", p(tape.obs[r]), p(tape.action[r]), p(tape.reward[r]), p(tape.done[r]),
@@ -154,7 +160,7 @@ def lpg_agent_train_step(k, tape: Tape, levels, step, lpg_params, lifetime_condi
     _lib.call("toued_agent_update", p(tape.obs[r]), p(tape.action[r]), p(tape.sorted_tok[r]), p(tape.pi_hat[a]),
               p(tape.y_hat[a]), p(tape.actor[t0]), p(tape.critic[t0]), p(tape.actor[t1]), p(tape.critic[t1]),
               p(levels), p(step), p(tape.scalars[a]), N, W, L, D, float(lr_actor), float(lr_critic),
-              float(max_grad_norm), float(agent_target_coeff), p(tape.agent_scratch), s)
+              float(max_grad_norm), float(agent_target_coeff), int(precopied), p(tape.agent_scratch), s)
     tape.scal_sum += tape.scalars[a]
 
 

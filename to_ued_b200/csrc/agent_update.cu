@@ -25,7 +25,7 @@ agent_update_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__
                     const float* __restrict__ critic_in, float* actor_out, float* critic_out,
                     const LevelRec* __restrict__ levels, int32_t* __restrict__ step,
                     float* __restrict__ scal, float* run_scratch, int n_agents, int W, int L, int D,
-                    float lr_a, float lr_c, float max_norm, float alpha) {
+                    float lr_a, float lr_c, float max_norm, float alpha, int tables_precopied) {
     extern __shared__ __align__(16) float smc[];          // [T][AU_C] records | scan | index   (106 KB at T = 1280: two CTAs per SM)
     __shared__ float red[32];
     __shared__ int iscan[512];
@@ -44,11 +44,14 @@ agent_update_kernel(const int32_t* __restrict__ obs, const uint8_t* __restrict__
     const float invT = 1.0f / (float)T;
     const SegIndex si = seg_index_build(idxmem, iscan, sorted_tok + (size_t)n * T, ob, T);
 
-    // dense copy theta_k -> theta_{k+1} (only touched rows change below)
-    for (int i = tid; i < D * 2; i += 256) {
-        reinterpret_cast<float4*>(a_out)[i] = reinterpret_cast<const float4*>(a_in)[i];
-        reinterpret_cast<float4*>(c_out)[i] = reinterpret_cast<const float4*>(c_in)[i];
-    }
+    // dense copy theta_k -> theta_{k+1} (only touched rows change below).  The production step makes this copy on a side
+    // stream while the LPG forward runs (tables_precopied: it is ~100 MB of pure traffic per launch, a third of this
+    // kernel's time, and depends on nothing but theta_k)
+    if (!tables_precopied)
+        for (int i = tid; i < D * 2; i += 256) {
+            reinterpret_cast<float4*>(a_out)[i] = reinterpret_cast<const float4*>(a_in)[i];
+            reinterpret_cast<float4*>(c_out)[i] = reinterpret_cast<const float4*>(c_in)[i];
+        }
 
     // ---- phase 0: per-token dlogits + metric partials -------------------------------------
     float m_kl = 0.f, m_pi2 = 0.f, m_y2 = 0.f;
@@ -176,8 +179,8 @@ extern "C" int toued_agent_update(const int32_t* obs, const uint8_t* action, con
                                   const float* critic_in, float* actor_out, float* critic_out,
                                   const void* levels, int32_t* step, float* scalars, int n_agents,
                                   int n_workers, int rollout_len, int obs_dim, float lr_actor,
-                                  float lr_critic, float max_grad_norm, float agent_target_coeff, float* run_scratch,
-                                  void* stream) {
+                                  float lr_critic, float max_grad_norm, float agent_target_coeff, int tables_precopied,
+                                  float* run_scratch, void* stream) {
     const int T = n_workers * rollout_len;
     const size_t smem = agent_smem_bytes(T, obs_dim);
     TOUED_CHECK(n_agents > 0 && T > 0, "toued_agent_update: empty problem");
@@ -190,7 +193,7 @@ extern "C" int toued_agent_update(const int32_t* obs, const uint8_t* action, con
     agent_update_kernel<<<n_agents, 256, smem, st>>>(
         obs, action, sorted_tok, pi_hat, y_hat, actor_in, critic_in, actor_out, critic_out,
         (const LevelRec*)levels, step, scalars, run_scratch, n_agents, n_workers, rollout_len, obs_dim,
-        lr_actor, lr_critic, max_grad_norm, agent_target_coeff);
+        lr_actor, lr_critic, max_grad_norm, agent_target_coeff, tables_precopied);
     TOUED_LAUNCH_CHECK();
     return 0;
 }
