@@ -285,6 +285,9 @@ int toued_tc_gemm_mixed_test(const float* A, const float* B, void* scratch_img, 
  * (the weight-gradient GEMM shape).  scratch_img: 64 KiB.                                           */
 int toued_tc_gemm_mn_test(const float* A, const float* B, void* scratch_img, float* D, int lbo, int sbo,
                           int kadv, void* stream);
+/* the same contraction on a CTA pair (cta_group::2, M = 256 over a 2-cluster): D f32[256][256] = A[128 k][256 m]^T B[128 k][256 n];
+ * scratch_img >= 128 KiB                                                                              */
+int toued_tc_gemm_mn2_test(const float* A, const float* B, void* scratch_img, float* D, void* stream);
 
 /* Pack the recurrent matrix Wh (+ input projection Wi, b_i) into the fp16 pass images the tensor-core
  * forward streams (wh_img: 16 x 26 KiB = 416 KiB, once per meta-step).                              */

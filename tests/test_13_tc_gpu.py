@@ -56,6 +56,22 @@ def test_tcgen05_mn_major_gemm_tile(built_lib):
     assert err < 2e-4, f"MN-major tcgen05 tile mismatch: max abs err {err}"
 
 
+def test_tcgen05_cta_pair_mn_major_gemm_tile(built_lib):
+    """cta_group::2: a 2-CTA cluster shares M256 N256 K16 MMAs (each CTA holds its 128 rows of A and half of B's N)."""
+    from to_ued_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(2)
+    A = torch.randn(128, 256, generator=g)          # [k][m]
+    B = torch.randn(128, 256, generator=g)          # [k][n]
+    img = torch.zeros(131072, dtype=torch.uint8, device="cuda")
+    D = torch.zeros(256, 256, device="cuda")
+    Ad, Bd = A.cuda(), B.cuda()
+    _lib.call("toued_tc_gemm_mn2_test", _lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(img), _lib.ptr(D), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    want = A.bfloat16().double().T @ B.bfloat16().double()
+    err = (D.cpu().double() - want).abs().max().item()
+    assert err < 4e-4, f"CTA-pair MN-major tcgen05 tile mismatch: max abs err {err}"
+
+
 @pytest.mark.parametrize("cond,n", [(False, 6), (True, 6), (False, 5), (True, 3)])
 def test_gru_forward_tc_matches_fp32_kernel_and_oracle(built_lib, cond, n):
     """Tensor-core GRU forward vs the exact-fp32 SIMT kernel on identical inputs.  Stated tolerance:

@@ -159,6 +159,76 @@ extern "C" int toued_tc_gemm_mn_test(const float* A, const float* B, void* scrat
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA pair (cta_group::2), both operands MN-major: D[256 m][256 n] = sum_k A[k][m] B[k][n], K = 128 tokens.
+// CTA r of the 2-cluster holds column groups {2r, 2r+1} of the A image (its 128 rows of M) and {2r, 2r+1} of the B image
+// (its half of N); the leader issues M256 N256 K16 MMAs; every CTA reads back its own 128 rows x 256 columns.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+tc_gemm_mn2_test_kernel(const unsigned char* __restrict__ Aimg, const unsigned char* __restrict__ Bimg, float* __restrict__ D) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* sA = smem;               // 2 token blocks x [2 col groups][8 KB]
+    unsigned char* sB = smem + 32768;
+    __shared__ __align__(8) uint64_t bar_ld, bar_peer, bar_mma;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t rank = cluster_ctarank();
+    if (tid == 0) { mbar_init(&bar_ld, 1); mbar_init(&bar_peer, 1); mbar_init(&bar_mma, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc2(&tmem_base, 256);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();                          // barriers of both CTAs are initialised before anyone arrives remotely
+    tc_fence_after();
+    const uint32_t tb = tmem_base;
+    if (tid == 0) {
+        mbar_expect_tx(&bar_ld, 65536);
+        for (int blk = 0; blk < 2; ++blk) {  // image: [token block][4 col groups][8 KB]
+            bulk_g2s(sA + blk * 16384, Aimg + ((size_t)(blk * 4 + 2 * rank) << 13), 16384, &bar_ld);
+            bulk_g2s(sB + blk * 16384, Bimg + ((size_t)(blk * 4 + 2 * rank) << 13), 16384, &bar_ld);
+        }
+        mbar_wait(&bar_ld, 0);
+        if (rank != 0) {
+            mbar_arrive_remote(&bar_peer, 0);            // my operands have landed: tell the leader
+        } else {
+            mbar_wait_cluster(&bar_peer, 0);
+            tc_fence_after();
+            constexpr uint32_t idesc = tc_idesc_mn(256, 256, 1);
+            for (int blk = 0; blk < 2; ++blk)
+                for (int ks = 0; ks < 4; ++ks)
+                    tc_mma2(tb, tc_smem_desc_mn(smem_u32(sA + blk * 16384 + ks * 2048), 8192),
+                            tc_smem_desc_mn(smem_u32(sB + blk * 16384 + ks * 2048), 8192), idesc, (blk | ks) != 0);
+            tc_commit2(&bar_mma, 3);
+        }
+    }
+    mbar_wait_cluster(&bar_mma, 0);
+    tc_fence_after();
+    for (int c = 0; c < 256; c += 8) {
+        float v[8];
+        tmem_ld8(tb + ((uint32_t)(warp * 32) << 16) + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) D[(size_t)(rank * 128 + tid) * 256 + c + e] = v[e];
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();                          // both CTAs are done with tensor memory before it is released
+    if (warp == 0) tmem_dealloc2(tb, 256);
+}
+
+extern "C" int toued_tc_gemm_mn2_test(const float* A, const float* B, void* scratch_img, float* D, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* ia = (unsigned char*)scratch_img;
+    unsigned char* ib = ia + 65536;
+    pack_tile_img_kernel<<<(128 * 256 + 255) / 256, 256, 0, st>>>(A, (__nv_bfloat16*)ia, 128, 256);
+    pack_tile_img_kernel<<<(128 * 256 + 255) / 256, 256, 0, st>>>(B, (__nv_bfloat16*)ib, 128, 256);
+    TOUED_LAUNCH_CHECK();
+    const size_t smem = 65536 + 1024;
+    TOUED_CUDA(cudaFuncSetAttribute(tc_gemm_mn2_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_gemm_mn2_test_kernel<<<2, 128, smem, st>>>(ia, ib, D);
+    TOUED_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K = 256 (SW128 blocks) + 16 (no-swizzle block): D[128][48] = A[128][272] * B[48][272]^T, fp16.
 __global__ void pack_b_mixed_kernel(const float* __restrict__ B, __half* __restrict__ img, int N, int K) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
