@@ -639,7 +639,195 @@ wgrad_pair_kernel(const unsigned char* __restrict__ hpimg, const unsigned char* 
     if (warp == 5) tmem_dealloc2(tmem_base, 512);
 }
 
-#if !defined(TOUED_WGRAD_PAIR)
+// ------------------------------------------------------------------------------------------------
+// TRANSPOSING version of the weight-gradient GEMMs (round 2; library variant "wgk", NOT the default -- measured slower:
+// 408 us per launch against 208 us.  Correct on every tensor-core parity test.  Per 64-token block a CTA moves 40 KB four
+// times through shared memory -- bulk-copy write, ldmatrix read, stmatrix write, tensor-core read = 160 KB, ~1,250 clk at
+// 128 B/clk, measured 1,877 clk -- which costs more than the MN-major ingestion it was meant to avoid.)
+// The MMAs of the kernels above take their
+// operands MN-major (contraction over tokens = rows of the token tile images) and run at 2.7 x their math time: the
+// tensor core ingests MN-major operands at ~20 elements per clock, whichever way the tile is cut (measured with the
+// CTA-pair kernel).  K-major operands stream at the math rate (gru_backward_tc: M128 N256 K16 in ~108 clk).  So this
+// kernel turns every 64-token x 64-column sub-tile around in shared memory before the MMA reads it:
+//   producer warp     bulk copies of the raw sub-tiles (as they lie in the images) into a 2-stage ring;
+//   4 transposer warps  ldmatrix.x4.trans + stmatrix.x4: four 8 x 8 blocks per instruction pair, raw [token][column] SW128 ->
+//                     K-major [column][token] SW128 tiles (2-stage ring), then fence.proxy.async + mbarrier;
+//   MMA warp          per 64-token block four K = 16 MMAs on K-major descriptors; commits release the K-major stage;
+//   the transposer warps are also the epilogue warps (TMEM -> partial sums, as above).
+// 12 tile types of equal cost (5 sub-tiles = 40 KB per token block): 8 dWh tiles (128 hidden units j x 192 gate columns c)
+// and 4 input-side tiles (the x group, M = 64, x 256 of the 1024 dG columns), 12 token splits each = 144 CTAs.
+constexpr int WK_THREADS = 192;            // 4 transposer / epilogue warps + producer warp + MMA warp
+constexpr int WK_SPLITS = 12;
+constexpr int WK_STAGE = 5 * 8192;         // 5 sub-tiles: A (2 for dWh: j groups; 1 for x) + B (3 for dWh; 4 for x)
+static_assert(WK_SPLITS <= 37, "Wh partial areas (lpg_backward.cu) are sized for 37 splits");
+
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void stsm_x4(uint32_t addr, const uint32_t (&r)[4]) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+
+__global__ void __launch_bounds__(WK_THREADS, 1)
+wgrad_kmajor_kernel(const unsigned char* __restrict__ hpimg, const unsigned char* __restrict__ dgimg,
+                    const unsigned char* __restrict__ ximg, float* __restrict__ partial, float* __restrict__ small_partial,
+                    const uint32_t* __restrict__ cotmax, int n_tok_blocks, int blocks_per_split, int accumulate) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* sRaw = smem;                             // 2 x 40 KB   raw sub-tiles [token][column]
+    unsigned char* sK = smem + 2 * WK_STAGE;                // 2 x 40 KB   K-major tiles [column][token]
+    __shared__ __align__(8) uint64_t raw_full[2], raw_empty[2], k_full[2], k_empty[2], done_bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // types 0-7: dWh tile (jt, cq): h'^T [128 j] x dG columns [192 cq, 192 cq + 192);  types 8-11: x^T x dG columns [256 xq, +256)
+    const int type = blockIdx.x % 12, split = blockIdx.x / 12;
+    const bool xt = type >= 8;
+    const int jt = type >> 2, cq = type & 3, xq = type - 8;
+    const int tb0 = split * blocks_per_split;
+    const int nblk = max(0, min(n_tok_blocks, tb0 + blocks_per_split) - tb0);
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); mbar_init(&k_full[s], 4); mbar_init(&k_empty[s], 1);
+        }
+        mbar_init(&done_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 5) tmem_alloc(&tmem_base_s, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 4) {
+        // ---- producer: raw sub-tiles.  Stage layout: dWh [A j-group 0 | A j-group 1 | B 3 column groups]; x [A x group | B 4 groups]
+        if (lane == 0) {
+            for (int i = 0; i < nblk; ++i) {
+                const int s = i & 1;
+                mbar_wait(&raw_empty[s], ((i >> 1) & 1) ^ 1);
+                mbar_expect_tx(&raw_full[s], WK_STAGE);
+                unsigned char* st = sRaw + s * WK_STAGE;
+                const size_t tb = (size_t)(tb0 + i);
+                if (!xt) {
+                    bulk_g2s(st, hpimg + ((tb * 4 + 2 * jt) << 13), 2 * 8192, &raw_full[s]);
+                    bulk_g2s(st + 2 * 8192, dgimg + ((tb * 16 + 3 * cq) << 13), 3 * 8192, &raw_full[s]);
+                } else {
+                    bulk_g2s(st, ximg + (tb << 13), 8192, &raw_full[s]);
+                    bulk_g2s(st + 8192, dgimg + ((tb * 16 + 4 * xq) << 13), 4 * 8192, &raw_full[s]);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ---- MMA issue on the K-major tiles (all lanes wait, one elected lane issues)
+        constexpr uint32_t idesc_wh = tc_idesc(128, 192, 0), idesc_x = tc_idesc(64, 256, 0);       // fp16, both operands K-major
+        for (int i = 0; i < nblk; ++i) {
+            const int s = i & 1;
+            mbar_wait(&k_full[s], (i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t k0 = smem_u32(sK + s * WK_STAGE);
+            if (elect_one()) {
+                const uint64_t ad = tc_smem_desc(k0), bd = tc_smem_desc(k0 + (xt ? 8192 : 2 * 8192));
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)                      // K = 16 tokens = 32 B along the 128-byte token rows
+                    tc_mma(tmem_base, ad + 2 * ks, bd + 2 * ks, xt ? idesc_x : idesc_wh, (i | ks) != 0);
+                tc_commit(&k_empty[s]);
+            }
+            __syncwarp();
+        }
+        if (elect_one()) tc_commit(&done_bar);
+        __syncwarp();
+    } else {
+        // ---- transposer warps: 5 sub-tiles x 16 groups of four 8 x 8 blocks, 20 groups per warp and token block
+        const int mi = lane >> 3, ri = lane & 7;
+        for (int i = 0; i < nblk; ++i) {
+            const int s = i & 1;
+            mbar_wait(&raw_full[s], (i >> 1) & 1);
+            mbar_wait(&k_empty[s], ((i >> 1) & 1) ^ 1);
+            const uint32_t src0 = smem_u32(sRaw + s * WK_STAGE), dst0 = smem_u32(sK + s * WK_STAGE);
+#pragma unroll 4
+            for (int g = warp; g < 80; g += 4) {
+                const int sub = g >> 4, gg = g & 15;
+                const int tc8 = gg >> 1, cc = (gg & 1) * 4 + mi;      // token chunk, column chunk of this lane's block
+                // source block: rows = tokens tc8*8 + ri, 16-byte chunk cc (swizzled by the row)
+                const uint32_t sa = src0 + sub * 8192 + (tc8 * 8 + ri) * 128 + ((cc ^ ri) << 4);
+                // destination block: rows = columns cc*8 + ri of the sub-tile, 16-byte chunk tc8 (swizzled by the row)
+                const uint32_t da = dst0 + sub * 8192 + (cc * 8 + ri) * 128 + ((tc8 ^ ri) << 4);
+                uint32_t r[4];
+                ldsm_x4_trans(sa, r);
+                stsm_x4(da, r);
+            }
+            fence_proxy_async_smem();                                 // generic-proxy stores -> tensor-core (async proxy) reads
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&raw_empty[s]); mbar_arrive(&k_full[s]); }
+        }
+        // ---- epilogue: TMEM lane = row of the tile
+        mbar_wait(&done_bar, 0);
+        tc_fence_after();
+        // the dG image is in units of the launch's cotangent scale S (tc.cuh): take it back out of the fp32 sums
+        const float inv_s = cotmax ? 1.0f / cot_scale_from_max(*cotmax) : 1.0f;
+        if (xt) {
+            // rows 0..7 of the x tile: dWi (rows q < X), dbi (row 7) and dbhn (row 7 of the dhn columns).
+            // Always accumulates: the head-gradient kernel has initialised this split's small-partial area.
+            if (warp == 0 && nblk > 0) {
+                float* out = small_partial + (size_t)split * SMT_TOTAL;
+                const int base = xq == 3 ? SMT_WI + lane * LPG_G + 512 : (xq == 2 ? SMT_BHN : SMT_WI + lane * LPG_G + 256 * xq);
+                const bool on = lane < 8 && (xq != 2 || lane == 7);
+                for (int c = 0; c < 256; c += 32) {          // 32 columns per round: loads first, then the stores
+                    float v[4][8], o[4][8];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tmem_ld8(tmem_base + c + 8 * k, v[k]);
+                    tmem_ld_wait();
+                    if (on) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) o[k][e] = out[base + c + 8 * k + e];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) out[base + c + 8 * k + e] = fmaf(v[k][e], inv_s, o[k][e]);
+                    }
+                }
+            }
+        } else {
+            const int j = jt * 128 + warp * 32 + lane;
+            float* out = partial + (size_t)split * LPG_H * LPG_G + (size_t)j * LPG_G + cq * 192;
+            // 64 columns per round: the previous partials are fetched with 16 independent loads in flight
+            for (int c = 0; c < 192; c += 64) {
+                float4 pre[16];
+                float4* p = reinterpret_cast<float4*>(out + c);
+                if (accumulate) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) pre[k] = p[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) pre[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float v[8];
+                    if (nblk > 0) {
+                        tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + c + 8 * k, v);
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                    }
+                    p[2 * k] = make_float4(fmaf(v[0], inv_s, pre[2 * k].x), fmaf(v[1], inv_s, pre[2 * k].y), fmaf(v[2], inv_s, pre[2 * k].z), fmaf(v[3], inv_s, pre[2 * k].w));
+                    p[2 * k + 1] = make_float4(fmaf(v[4], inv_s, pre[2 * k + 1].x), fmaf(v[5], inv_s, pre[2 * k + 1].y), fmaf(v[6], inv_s, pre[2 * k + 1].z), fmaf(v[7], inv_s, pre[2 * k + 1].w));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 256);
+}
+
+#if defined(TOUED_WGRAD_KMAJOR)
+constexpr int WT_SPLITS = WK_SPLITS;       // 12 tile types x 12 = 144 CTAs
+#elif !defined(TOUED_WGRAD_PAIR)
 constexpr int WT_SPLITS = 24;              // 6 tile types x 24 = 144 CTAs
 #else
 constexpr int WT_SPLITS = WP_S1;           // dWh partial areas written by the pair kernel
@@ -674,7 +862,13 @@ extern "C" int toued_lpg_wgrad_tc(const void* hpimg, const void* dgimg, const vo
                                                                          cotangent_max, R, L, rbps, accumulate);
     }
     TOUED_LAUNCH_CHECK();
-#if !defined(TOUED_WGRAD_PAIR)
+#if defined(TOUED_WGRAD_KMAJOR)
+    const size_t smem = 4 * WK_STAGE + 1024;
+    TOUED_CUDA(cudaFuncSetAttribute(wgrad_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad_kmajor_kernel<<<12 * WK_SPLITS, WK_THREADS, smem, st>>>((const unsigned char*)hpimg, (const unsigned char*)dgimg,
+                                                                  (const unsigned char*)ximg, wh_partials, small_partials,
+                                                                  cotangent_max, n_tb, bps, accumulate);
+#elif !defined(TOUED_WGRAD_PAIR)
     const size_t smem = WT_NS * WT_STAGE + 1024;
     TOUED_CUDA(cudaFuncSetAttribute(wgrad_wh_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wgrad_wh_tc_kernel<<<6 * WT_SPLITS, WT_THREADS, smem, st>>>((const unsigned char*)hpimg, (const unsigned char*)dgimg,
