@@ -109,3 +109,20 @@ def test_mini_batches_and_sharding_are_exact_partitions(built_lib, fp32_gru):
         (_, _, _, mr), _ = _run(cr, K, n_global=4, offset=2 * r)
         gs.append(mr["_grad"].clone())
     assert rel_err((gs[0] + gs[1]).cpu().numpy(), g1.cpu().numpy()) < 2e-6
+
+
+def test_side_stream_plan_equals_serial_enqueue(built_lib, monkeypatch):
+    """The production stream plan (token sort, the dense theta_k -> theta_{k+1} table copy, the agent adjoint and the
+    embedding gradient on side streams; ``tables_precopied``) against everything enqueued on one stream with the copy
+    inside toued_agent_update: bit-identical gradient, tables, step counters and metrics."""
+    import to_ued_b200
+    K, n = 5, 6
+    res = {}
+    for side in (True, False):
+        monkeypatch.setattr(to_ued_b200, "SIDE_STREAMS", side)
+        c = Case("all_shortlife", n=n, seed=11, table_scale=0.3, lifetimes=[250, 3, 250, 250, 1, 250], steps=[0, 0, 17, 246, 0, 5])
+        (new_ts, ag2, vc2, met), ws = _run(c, K)
+        res[side] = (met["_grad"].cpu().numpy(), ag2.actor_state.params.cpu().numpy(), ag2.critic_state.params.cpu().numpy(),
+                     ag2.actor_state.step.cpu().numpy(), float(met["lpg_loss"]), float(met["lpg_agent"]["policy_entropy"]))
+    for a, b in zip(res[True], res[False]):
+        np.testing.assert_array_equal(a, b)

@@ -1,6 +1,6 @@
 // Tensor-core GRU forward (tcgen05 / TMEM / TMA), the production path for models/lpg.py:11-30,77-84.
 //
-// A CTA owns 128 sequences (UMMA_M = 128, cta_group::1) for all L reverse-scan steps; 18 warps, warp-specialised.
+// A CTA owns 128 sequences (UMMA_M = 128, cta_group::1) for all L reverse-scan steps; 19 warps, warp-specialised.
 //   * Hidden state: lives in TENSOR MEMORY as fp16 pairs (2 x 128 columns, ping-pong over the steps) and is the
 //     TMEM-resident A operand of the recurrent MMAs (tcgen05.mma with [a_tmem]).  It never touches shared memory: a
 //     64 KB smem A tile re-read by each of the 16 passes of a step was the bound of the first version (the tensor core
@@ -42,7 +42,13 @@ constexpr int FT_AX = (FT_M / 8) * 256;            // 4096 B: x tile of the A op
 constexpr int FT_NS = 6;                  // B stages
 constexpr int FT_THEADS = 128, FT_TTILE = 192, FT_THOLD = 256;   // tensor-memory columns: 2 x 64 gate accumulators at 0, 2 x 32 head
                                                                  // accumulators, 4 x 8 relu(h) tiles, 2 x 128 columns of hidden state
-constexpr int FT_THREADS = 576;           // 2 sets of 8 epilogue warps (even / odd passes) + producer warp + MMA warp
+// FT_HEADS_WARP: the heads MMAs (one K = 16 MMA per pass on the relu(h) tile) are issued by a warp of their own instead of
+// by the gate-MMA warp "a few passes behind": the gate-MMA warp is a serial resource (16 passes x ~200 uniform-datapath
+// instructions and three barrier waits per step) and the epilogue warps spend 20 % of their time waiting for its MMAs.
+#ifndef FT_HEADS_WARP
+#define FT_HEADS_WARP 1
+#endif
+constexpr int FT_THREADS = 576 + 32 * FT_HEADS_WARP;   // 2 sets of 8 epilogue warps (even / odd passes) + producer warp + MMA warp (+ heads-MMA warp)
 
 // Wh[k][c] (fp32, c = g*256 + unit) -> fp16 pass images: image[p][kb][row = g*16 + u][128 B swizzled]
 __global__ void pack_wh_fwd_kernel(const float* __restrict__ Wh, __half* __restrict__ img, size_t lpg_stride) {
@@ -236,14 +242,41 @@ gru_forward_tc_kernel(const float* __restrict__ x, const uint8_t* __restrict__ d
                         tc_commit(&acc_full[a]);
                     }
                     __syncwarp();
+#if !FT_HEADS_WARP
                     while (hq + 4 <= it) issue_heads(hq++);
+#endif
                 }
+#if !FT_HEADS_WARP
                 // the step's last heads MMAs: must not wait for the next step (the epilogue warps need the tile
                 // buffers back to finish this one)
                 while (hq < it) issue_heads(hq++);
+#else
+                (void)hq; (void)issue_heads;
+#endif
                 cur ^= 1;
             }
         }
+#if FT_HEADS_WARP
+    } else if (warp == 18) {
+        // ===================== heads-MMA issuer: follows the relu(h) tiles as the epilogue warps publish them.  Ordering with
+        // the readout of the head accumulators two steps earlier is transitive: readout(s) precedes that warp's passes of step
+        // s + 1, hence a_ready(s + 1), hence the gate MMAs and relu tiles of step s + 2 this warp waits for.
+        constexpr uint32_t idesc_h = tc_idesc(FT_M, 32, 0);
+        const uint32_t hb_addr = smem_u32(sHB);
+        const uint32_t nq = (uint32_t)L * FT_NPASS;
+        for (uint32_t q = 0; q < nq; ++q) {
+            const uint32_t sb = q & 3, p = q & 15, stp = q >> 4;
+            mbar_wait(&stage_full[sb], (q >> 2) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                tc_mma_ts(tmem_base + FT_THEADS + (stp & 1) * 32, tmem_base + FT_TTILE + sb * 8, tc_smem_desc_k16(hb_addr + p * 1024),
+                          idesc_h, p != 0);
+                tc_commit(&stage_empty[sb]);
+                if (p == 15) tc_commit(&heads_full[stp & 1]);
+            }
+            __syncwarp();
+        }
+#endif
     } else {
         // ===================== epilogue warps: set 0 (warps 0..7) takes the even passes / accumulator 0,
         // set 1 (warps 8..15) the odd passes / accumulator 1.  A pass is one long dependent chain per warp
