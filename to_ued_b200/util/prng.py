@@ -51,7 +51,7 @@ def _native_iota_bits():
 def iota_bits(key, n: int) -> np.ndarray:
     """threefry_2x32(key, iota(n)): uint32[..., 2] -> uint32[..., n]"""
     key = np.asarray(key, np.uint32)
-    fn = _native_iota_bits() if key.size >= 8 else False          # batched keys: native host loop
+    fn = _native_iota_bits() if (key.size >= 8 or n >= 64) else False   # batched keys / long draws: native host loop
     if fn:
         k2 = np.ascontiguousarray(key.reshape(-1, 2))
         out = np.empty((k2.shape[0], n), np.uint32)
