@@ -1,7 +1,7 @@
 """Which quantisation explains the tensor-core path's meta-gradient error?  CPU experiment on the fp64 oracle with
-straight-through fp16 rounding injected into the GRU forward (a measurement tool; not part of the product or the tests; only tools, tests and bench may import oracle/)."""
+straight-through fp16 rounding injected into the GRU forward (a diagnostic next to the tests, like tests/diag_probe.py: only tests/, smoke() and bench.py may import oracle/)."""
 import sys, os
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..")); sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..")); sys.path.insert(0, os.path.dirname(__file__))
 import numpy as np, torch
 import oracle.lpg as olpg
 import oracle.agents as oag_mod
