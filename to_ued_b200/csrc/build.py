@@ -31,6 +31,7 @@ VARIANTS = {
     "wgpair": ["-DTOUED_WGRAD_PAIR=1"],      # cta_group::2: CTA pairs sharing M256 N256 MMAs
     "wpprobe": ["-DTOUED_WGRAD_PAIR=1", "-DTOUED_WP_PROBE=1"],   # the same with a launch-size override for timing experiments
     "wgk": ["-DTOUED_WGRAD_KMAJOR=1"],       # K-major operands transposed in shared memory (ldmatrix.trans / stmatrix)
+    "fwdns7": ["-DFT_NS_OVERRIDE=7"],        # gru_forward_tc with 7 instead of 6 weight stages in flight
     "fwd1": ["-DFT_HEADS_WARP=0"],           # gru_forward_tc with the heads MMAs issued by the gate-MMA warp (round-1 arrangement)
     "pf2": ["-DBT_PF_DEPTH=2"],              # gru_backward_tc with two chunks of saved activations in flight per thread
     "pf": ["-DBT_L2_PREFETCH=1"],            # gru_backward_tc with an L2 bulk prefetch of the next step's saved activations (measured slower)

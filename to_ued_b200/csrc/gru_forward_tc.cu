@@ -39,7 +39,11 @@ constexpr int FT_XN = 64;                          // x-part rows: Wi_r, Wi_z, 0
 constexpr int FT_BX = (FT_XN / 8) * 256;           // 2048 B: input part (no-swizzle K=16 block: x[0..7] incl. the bias 1)
 constexpr int FT_BSTAGE = FT_BH + FT_BX;           // 26624 B per pass image (multiple of 1024)
 constexpr int FT_AX = (FT_M / 8) * 256;            // 4096 B: x tile of the A operand
-constexpr int FT_NS = 6;                  // B stages
+#ifndef FT_NS_OVERRIDE
+constexpr int FT_NS = 6;                  // B stages (7 measured: see DESIGN.md section 7.0)
+#else
+constexpr int FT_NS = FT_NS_OVERRIDE;
+#endif
 constexpr int FT_THEADS = 128, FT_TTILE = 192, FT_THOLD = 256;   // tensor-memory columns: 2 x 64 gate accumulators at 0, 2 x 32 head
                                                                  // accumulators, 4 x 8 relu(h) tiles, 2 x 128 columns of hidden state
 // FT_HEADS_WARP: the heads MMAs (one K = 16 MMA per pass on the relu(h) tile) are issued by a warp of their own instead of
