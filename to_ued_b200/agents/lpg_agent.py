@@ -113,6 +113,15 @@ def _sort_stream(cur):
     return st
 
 
+def _mark(label):
+    """Fine-grained device timeline (tools/phase_timeline.py FINE=1): an event on the current stream; no-op in production."""
+    import to_ued_b200
+    if to_ued_b200.PHASE_EVENTS is not None and getattr(to_ued_b200, "PHASE_FINE", False):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream())
+        to_ued_b200.PHASE_EVENTS.append((label, -2, e))
+
+
 def lpg_agent_train_step(k, tape: Tape, levels, step, lpg_params, lifetime_conditioning, agent_target_coeff,
                          lr_actor, lr_critic, max_grad_norm, lpg_stride=0):
     """agents/lpg_agent.py:31-85 for update ``k`` of the tape: reads theta_k / phi_k and the k-th rollout,
@@ -137,6 +146,7 @@ def lpg_agent_train_step(k, tape: Tape, levels, step, lpg_params, lifetime_condi
             tape.actor[t1].copy_(tape.actor[t0])
             tape.critic[t1].copy_(tape.critic[t0])
         ev_sort.record(side)
+    _mark("rollout")
     tape.step_in[a].copy_(step)
     _lib.call("toued_lpg_prepare", p(tape.obs[r]), p(tape.action[r]), p(tape.reward[r]), p(tape.done[r]),
               p(tape.actor[t0]), p(tape.critic[t0]), p(lpg_params), p(step), p(levels), p(tape.x[a]),
@@ -156,12 +166,15 @@ def lpg_agent_train_step(k, tape: Tape, levels, step, lpg_params, lifetime_condi
                   p(tape.h16[a]), p(tape.fac[a]) if tape.fac is not None else None,
                   p(tape.hpimg[a]) if tape.hpimg is not None else None, p(tape.pi_hat[a]), p(tape.y_hat[a]),
                   N, W, L, int(lifetime_conditioning), s)
+    _mark("gru_fwd")
     cur.wait_event(ev_sort)
+    _mark("sort_wait")
     _lib.call("toued_agent_update", p(tape.obs[r]), p(tape.action[r]), p(tape.sorted_tok[r]), p(tape.pi_hat[a]),
               p(tape.y_hat[a]), p(tape.actor[t0]), p(tape.critic[t0]), p(tape.actor[t1]), p(tape.critic[t1]),
               p(levels), p(step), p(tape.scalars[a]), N, W, L, D, float(lr_actor), float(lr_critic),
               float(max_grad_norm), float(agent_target_coeff), int(precopied), p(tape.agent_scratch), s)
     tape.scal_sum += tape.scalars[a]
+    _mark("update")
 
 
 def train_lpg_agent_steps(rng, lpg_train_state, agent_state: AgentState, rollout_manager, num_train_steps: int,

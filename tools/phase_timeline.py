@@ -20,6 +20,7 @@ from to_ued_b200.meta.meta import create_lpg_train_state, make_lpg_train_step  #
 
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+    to_ued_b200.PHASE_FINE = os.environ.get("FINE", "0") != "0"
     args = parse_args(["--env_mode", "all_shortlife", "--num_agents", os.environ.get("TOUED_AGENTS", "512"), "--num_mini_batches",
                        os.environ.get("TOUED_BENCH_MINI_BATCHES", "2")])
     rng = prng.PRNGKey(args.seed)
@@ -59,6 +60,10 @@ def main():
         t_prev_end = end
     evs = per_step[-1]
     start = evs[0][2]
+    fine = [(lab, e) for lab, c, e in evs if c == -2]
+    if fine:                                              # FINE=1: inside the agent updates (one chunk)
+        prev = start
+        print("fine: " + "  ".join(f"{lab} +{(lambda d: d)(prev.elapsed_time(e)):.3f}" + ("" if (prev := e) is None else "") for lab, e in fine))
     chunks = sorted({c for _, c, _ in evs if c >= 0})
     for c in chunks:
         print(f"chunk {c}: " + "  ".join(f"{lab} {start.elapsed_time(e):.2f}" for lab, cc, e in evs if cc == c))
